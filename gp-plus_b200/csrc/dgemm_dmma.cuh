@@ -1,0 +1,280 @@
+// FP64 tensor-core (DMMA m8n8k4) tile GEMM for sm_100a.
+//
+// One kernel family serves every O(N^3) step of the exact-GP hot path:
+//   Cholesky TRSM / SYRK trailing updates, the recursive-doubling triangular inverse and
+//   K^-1 = L^-T L^-1 (replacing torch.linalg.cholesky + autograd's cholesky_backward that the
+//   reference reaches through gpytorch, optim/mll_scipy.py:37-39,123).
+//
+//   C[ti,tj] = beta*C[ti,tj] + alpha * sum_{kb in [klo,khi)} A(ti,kb) * B(tj,kb)^T
+//
+// with 128x128 output tiles, operands in either "k-contiguous" ([row][k]) or
+// "k-strided" ([k][row]) row-major layout, a per-tile K range that can depend on the tile
+// row / column (triangular operands are skipped, not multiplied by zeros), an optional
+// lower-triangle tile filter and a batch dimension.  tcgen05 has no FP64 kind, so the
+// tensor-core path for doubles on Blackwell is mma.sync DMMA; sm_100a lowers every f64
+// mma shape to DMMA.8x8x4 (checked with cuobjdump), which is what is issued here.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gpp {
+
+constexpr int TILE = 128;        // output tile edge and K block
+constexpr int BK = 16;           // k-chunk staged per pipeline stage
+constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_STAGES = 4;
+constexpr int LDS_KC = BK + 4;   // [row][k] smem row stride (doubles): banks (8g+2t) conflict-free
+constexpr int LDS_KS = TILE + 4; // [k][row] smem row stride (doubles)
+constexpr int STAGE_ELEMS_KC = TILE * LDS_KC;  // 2560
+constexpr int STAGE_ELEMS_KS = BK * LDS_KS;    // 2112
+constexpr int STAGE_ELEMS = STAGE_ELEMS_KC;    // per operand, max of both layouts
+constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * 2 * STAGE_ELEMS * 8;  // 163840
+
+enum KSel { KSEL_CONST = 0, KSEL_TI = 1, KSEL_TJ = 2 };
+enum TileMap { MAP_RECT = 0, MAP_TRI = 1 };
+enum Epilogue { EPI_STORE = 0, EPI_ROWSQ = 2 };
+
+struct GemmOp {
+    const double* A;
+    const double* B;
+    double* C;
+    int lda, ldb, ldc;
+    long long a_zs, b_zs, c_zs;  // batch strides in elements
+    int tiles_m, tiles_n;        // region size in tiles
+    int tiles_m_last;            // tiles_m of the last batch entry
+    int map;                     // TileMap
+    int lower_filter;            // rect map: keep tile iff ti + lower_off >= tj
+    int lower_off;
+    int klo_sel, klo_c;          // K range in 128-blocks: klo = klo_c + sel(ti|tj)
+    int khi_sel, khi_c;          //                         khi = khi_c + sel(ti|tj)
+    double alpha, beta;
+    int mirror;                  // also store the transposed tile at (tj,ti) (K^-1 full storage)
+    int epilogue;                // Epilogue
+    double* rowsq;               // EPI_ROWSQ: rowsq[tj * rowsq_ld + global_row] = sum_n acc[row][n]^2
+    int rowsq_ld;
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// stage one 128 x BK operand chunk into shared memory with 16-byte cp.async
+template <bool KC>
+__device__ __forceinline__ void load_chunk(double* sm, const double* g, int ld, int tid) {
+    if (KC) {
+        // global: row r (128 rows), 16 contiguous doubles -> 8 x 16B per row
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            int c = tid + i * GEMM_THREADS;
+            int r = c >> 3, q = c & 7;
+            cp_async16(sm + r * LDS_KC + q * 2, g + (long long)r * ld + q * 2);
+        }
+    } else {
+        // global: k row (16 rows), 128 contiguous doubles -> 64 x 16B per row
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            int c = tid + i * GEMM_THREADS;
+            int r = c >> 6, q = c & 63;
+            cp_async16(sm + r * LDS_KS + q * 2, g + (long long)r * ld + q * 2);
+        }
+    }
+}
+
+template <bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_dmma_kernel(const GemmOp op) {
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x;
+    const int z = blockIdx.y;
+    const int tm = (z == (int)gridDim.y - 1) ? op.tiles_m_last : op.tiles_m;
+
+    int ti, tj;
+    if (op.map == MAP_TRI) {
+        // bid -> (ti,tj), tj <= ti, ti ascending (tiles with the longest K range first for LAUUM)
+        int bid = blockIdx.x;
+        int t = (int)((sqrt(8.0 * (double)bid + 1.0) - 1.0) * 0.5);
+        while ((long long)(t + 1) * (t + 2) / 2 <= bid) t++;
+        while ((long long)t * (t + 1) / 2 > bid) t--;
+        ti = t;
+        tj = bid - (int)((long long)t * (t + 1) / 2);
+        if (ti >= tm) return;
+    } else {
+        ti = blockIdx.x / op.tiles_n;
+        tj = blockIdx.x - ti * op.tiles_n;
+        if (ti >= tm) return;
+        if (op.lower_filter && (ti + op.lower_off < tj)) return;
+    }
+
+    int klo = op.klo_c + (op.klo_sel == KSEL_TI ? ti : (op.klo_sel == KSEL_TJ ? tj : 0));
+    int khi = op.khi_c + (op.khi_sel == KSEL_TI ? ti : (op.khi_sel == KSEL_TJ ? tj : 0));
+    const int nch = (khi > klo) ? (khi - klo) * (TILE / BK) : 0;
+
+    const double* Ag = op.A + (long long)z * op.a_zs;
+    const double* Bg = op.B + (long long)z * op.b_zs;
+    long long a_step, b_step;  // pointer advance per k-chunk
+    if (A_KC) { Ag += (long long)ti * TILE * op.lda + (long long)klo * TILE; a_step = BK; }
+    else      { Ag += (long long)klo * TILE * op.lda + (long long)ti * TILE; a_step = (long long)BK * op.lda; }
+    if (B_KC) { Bg += (long long)tj * TILE * op.ldb + (long long)klo * TILE; b_step = BK; }
+    else      { Bg += (long long)klo * TILE * op.ldb + (long long)tj * TILE; b_step = (long long)BK * op.ldb; }
+
+    double* sA = smem;
+    double* sB = smem + GEMM_STAGES * STAGE_ELEMS;
+
+    const int warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm0 = (warp >> 1) * 32;  // 4 warps along M
+    const int wn0 = (warp & 1) * 64;   // 2 warps along N
+
+    double acc[4][8][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+    // prologue: S-1 chunks in flight
+#pragma unroll
+    for (int s = 0; s < GEMM_STAGES - 1; s++) {
+        if (s < nch) {
+            load_chunk<A_KC>(sA + s * STAGE_ELEMS, Ag + s * a_step, op.lda, tid);
+            load_chunk<B_KC>(sB + s * STAGE_ELEMS, Bg + s * b_step, op.ldb, tid);
+        }
+        cp_async_commit();
+    }
+
+    for (int c = 0; c < nch; c++) {
+        cp_async_wait<GEMM_STAGES - 2>();
+        __syncthreads();
+        {
+            int cn = c + GEMM_STAGES - 1;
+            if (cn < nch) {
+                int s = cn % GEMM_STAGES;
+                load_chunk<A_KC>(sA + s * STAGE_ELEMS, Ag + cn * a_step, op.lda, tid);
+                load_chunk<B_KC>(sB + s * STAGE_ELEMS, Bg + cn * b_step, op.ldb, tid);
+            }
+            cp_async_commit();
+        }
+        const double* a_s = sA + (c % GEMM_STAGES) * STAGE_ELEMS;
+        const double* b_s = sB + (c % GEMM_STAGES) * STAGE_ELEMS;
+#pragma unroll
+        for (int kk = 0; kk < BK / 4; kk++) {
+            double af[4], bf[8];
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++) {
+                if (A_KC) af[mi] = a_s[(wm0 + mi * 8 + g) * LDS_KC + kk * 4 + t];
+                else      af[mi] = a_s[(kk * 4 + t) * LDS_KS + wm0 + mi * 8 + g];
+            }
+#pragma unroll
+            for (int ni = 0; ni < 8; ni++) {
+                if (B_KC) bf[ni] = b_s[(wn0 + ni * 8 + g) * LDS_KC + kk * 4 + t];
+                else      bf[ni] = b_s[(kk * 4 + t) * LDS_KS + wn0 + ni * 8 + g];
+            }
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+                for (int ni = 0; ni < 8; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();  // every operand read of this CTA is complete (C may alias A)
+
+    const double alpha = op.alpha, beta = op.beta;
+    if (op.epilogue == EPI_ROWSQ) {
+        // rowsq[tj][row] = sum over the tile's 128 columns of (alpha*acc)^2 ; reduce t-lanes then the 2 N-warps
+        double* red = smem;  // [2][128]
+#pragma unroll
+        for (int mi = 0; mi < 4; mi++) {
+            double s = 0.0;
+#pragma unroll
+            for (int ni = 0; ni < 8; ni++) {
+                double v0 = alpha * acc[mi][ni][0], v1 = alpha * acc[mi][ni][1];
+                s = fma(v0, v0, s);
+                s = fma(v1, v1, s);
+            }
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            if (t == 0) red[(warp & 1) * TILE + wm0 + mi * 8 + g] = s;
+        }
+        __syncthreads();
+        if (tid < TILE) {
+            double s = red[tid] + red[TILE + tid];
+            op.rowsq[(long long)tj * op.rowsq_ld + (long long)z * op.c_zs + (long long)ti * TILE + tid] = s;
+        }
+        return;
+    }
+
+    double* Cg = op.C + (long long)z * op.c_zs + (long long)ti * TILE * op.ldc + (long long)tj * TILE;
+    double* Ct = op.C + (long long)z * op.c_zs + (long long)tj * TILE * op.ldc + (long long)ti * TILE;
+    const bool do_mirror = op.mirror && (ti != tj);
+#pragma unroll
+    for (int mi = 0; mi < 4; mi++) {
+#pragma unroll
+        for (int ni = 0; ni < 8; ni++) {
+            int r = wm0 + mi * 8 + g;
+            int cidx = wn0 + ni * 8 + 2 * t;
+            double2* p = reinterpret_cast<double2*>(Cg + (long long)r * op.ldc + cidx);
+            double2 v;
+            v.x = alpha * acc[mi][ni][0];
+            v.y = alpha * acc[mi][ni][1];
+            if (beta != 0.0) {
+                double2 o = *p;
+                v.x = fma(beta, o.x, v.x);
+                v.y = fma(beta, o.y, v.y);
+            }
+            *p = v;
+            if (do_mirror) {
+                Ct[(long long)cidx * op.ldc + r] = v.x;
+                Ct[(long long)(cidx + 1) * op.ldc + r] = v.y;
+            }
+        }
+    }
+}
+
+inline cudaError_t launch_gemm(const GemmOp& op, bool a_kc, bool b_kc, int nbatch, cudaStream_t st) {
+    int nt;
+    if (op.map == MAP_TRI) nt = op.tiles_m * (op.tiles_m + 1) / 2;
+    else nt = op.tiles_m * op.tiles_n;
+    if (nt <= 0 || nbatch <= 0) return cudaSuccess;
+    dim3 grid(nt, nbatch), block(GEMM_THREADS);
+    if (a_kc && b_kc) dgemm_dmma_kernel<true, true><<<grid, block, GEMM_SMEM_BYTES, st>>>(op);
+    else if (a_kc && !b_kc) dgemm_dmma_kernel<true, false><<<grid, block, GEMM_SMEM_BYTES, st>>>(op);
+    else if (!a_kc && !b_kc) dgemm_dmma_kernel<false, false><<<grid, block, GEMM_SMEM_BYTES, st>>>(op);
+    else dgemm_dmma_kernel<false, true><<<grid, block, GEMM_SMEM_BYTES, st>>>(op);
+    return cudaGetLastError();
+}
+
+inline cudaError_t gemm_set_attributes() {
+    cudaError_t e;
+    e = cudaFuncSetAttribute(dgemm_dmma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(dgemm_dmma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(dgemm_dmma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(dgemm_dmma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+    return e;
+}
+
+inline GemmOp gemm_default() {
+    GemmOp op{};
+    op.alpha = 1.0;
+    op.beta = 0.0;
+    op.map = MAP_RECT;
+    op.klo_sel = KSEL_CONST;
+    op.khi_sel = KSEL_CONST;
+    op.tiles_n = 1;
+    op.epilogue = EPI_STORE;
+    return op;
+}
+
+}  // namespace gpp

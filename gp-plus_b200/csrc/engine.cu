@@ -1,0 +1,867 @@
+// C-ABI engine: exact-GP MLL + gradient, factorisation, batched prediction and acquisition arg-max
+// on one B200 (sm_100a).  Entry points are declared (with the reference call sites they replace) in
+// include/gpplus_b200.h.  There is no CPU fallback anywhere in this file.
+#include "../../include/gpplus_b200.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "chol.cuh"
+#include "cov.cuh"
+#include "predict.cuh"
+#include "solve.cuh"
+
+using namespace gpp;
+
+static thread_local std::string g_err;
+
+static void set_err(const char* what, cudaError_t e) {
+    char buf[512];
+    snprintf(buf, sizeof(buf), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    g_err = buf;
+}
+
+#define CK(x)                         \
+    do {                              \
+        cudaError_t e_ = (x);         \
+        if (e_ != cudaSuccess) {      \
+            set_err(#x, e_);          \
+            return GPP_ERR_CUDA;      \
+        }                             \
+    } while (0)
+
+#define ARG_FAIL(msg)       \
+    do {                    \
+        g_err = msg;        \
+        return GPP_ERR_ARG; \
+    } while (0)
+
+enum { EV_START = 0, EV_COV, EV_CHOL, EV_TRTRI, EV_SOLVE, EV_LAUUM, EV_GRAD, EV_END, EV_COUNT };
+
+struct gpp_handle {
+    int device = 0;
+    cudaStream_t st = nullptr;
+    long long n = 0, np = 0;
+    int T = 0;
+    int dq = 0, dqp = 0, dz = 0, n_combo = 0, n_noise = 0, n_mean = 0, kernel = 0;
+    // static training data
+    double *xq = nullptr, *y = nullptr, *centre = nullptr;
+    int *level_idx = nullptr, *noise_idx = nullptr, *mean_idx = nullptr;
+    // hyper-parameters (device copy): [w dq | ztab n_combo*dz | noise | beta]
+    double* hyp = nullptr;
+    double* hyp_host = nullptr;  // pinned
+    int hyp_len = 0;
+    double sf2 = 0.0;
+    // per-evaluation point panels
+    double *xs = nullptr, *nrm = nullptr, *zpt = nullptr, *r = nullptr, *diag_add = nullptr;
+    double *v = nullptr, *alpha = nullptr, *part = nullptr;
+    // N x N work matrices
+    double *A = nullptr, *M = nullptr, *S = nullptr;
+    double* logdet_part = nullptr;
+    int* info = nullptr;
+    int* info_host = nullptr;  // pinned
+    double *tile_part = nullptr, *zpart = nullptr, *gz = nullptr;
+    double* res = nullptr;
+    double* res_host = nullptr;  // pinned
+    double* gz_host = nullptr;   // pinned
+    int res_len = 0;
+    std::vector<int> level_idx_host;
+    // prediction chunk buffers
+    long long mc_alloc = 0;
+    double *c_xq = nullptr, *c_xs = nullptr, *c_nrm = nullptr, *c_zpt = nullptr, *c_K = nullptr;
+    int *c_lvl = nullptr, *c_noise = nullptr, *c_mean = nullptr, *c_cost = nullptr;
+    double *c_mean_part = nullptr, *c_rowsq = nullptr, *c_mu = nullptr, *c_var = nullptr, *c_score = nullptr;
+    double* c_blk_best = nullptr;
+    long long* c_blk_idx = nullptr;
+    double* acq_par = nullptr;  // [cost n_cost | best_f n_cost]
+    int* acq_kind = nullptr;
+    int acq_cap = 0;
+    bool factorized = false;
+    double last_jitter = 0.0;
+    cudaEvent_t ev[EV_COUNT];
+    bool ev_valid[EV_COUNT];
+    gpp_timings tm;
+};
+
+static const double* hyp_w(const gpp_handle* h) { return h->hyp; }
+static const double* hyp_z(const gpp_handle* h) { return h->hyp + h->dq; }
+static const double* hyp_noise(const gpp_handle* h) { return h->hyp + h->dq + h->n_combo * h->dz; }
+static const double* hyp_beta(const gpp_handle* h) { return h->hyp + h->dq + h->n_combo * h->dz + h->n_noise; }
+
+extern "C" int gpp_version(void) { return 100; }
+
+extern "C" int gpp_device_count(void) {
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return c;
+}
+
+extern "C" const char* gpp_last_error(void) { return g_err.c_str(); }
+
+template <typename Tp>
+static cudaError_t dev_alloc(Tp** p, size_t count) {
+    return cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(Tp));
+}
+
+extern "C" void gpp_destroy(gpp_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->st) cudaStreamSynchronize(h->st);
+    void* dptrs[] = {h->xq, h->y, h->centre, h->level_idx, h->noise_idx, h->mean_idx, h->hyp, h->xs, h->nrm, h->zpt,
+                     h->r, h->diag_add, h->v, h->alpha, h->part, h->A, h->M, h->S, h->logdet_part, h->info,
+                     h->tile_part, h->zpart, h->gz, h->res, h->c_xq, h->c_xs, h->c_nrm, h->c_zpt, h->c_K, h->c_lvl,
+                     h->c_noise, h->c_mean, h->c_cost, h->c_mean_part, h->c_rowsq, h->c_mu, h->c_var, h->c_score,
+                     h->c_blk_best, h->c_blk_idx, h->acq_par, h->acq_kind};
+    for (void* p : dptrs)
+        if (p) cudaFree(p);
+    if (h->hyp_host) cudaFreeHost(h->hyp_host);
+    if (h->info_host) cudaFreeHost(h->info_host);
+    if (h->res_host) cudaFreeHost(h->res_host);
+    if (h->gz_host) cudaFreeHost(h->gz_host);
+    for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(h->ev[i]);
+    if (h->st) cudaStreamDestroy(h->st);
+    delete h;
+}
+
+extern "C" int gpp_create(const gpp_problem* p, int device, gpp_handle** out) {
+    if (!p || !out) ARG_FAIL("gpp_create: null argument");
+    *out = nullptr;
+    if (p->n <= 0 || p->n > (1 << 20)) ARG_FAIL("gpp_create: n out of range");
+    if (p->dq < 0 || p->dq > GPP_MAX_DQ) ARG_FAIL("gpp_create: dq out of range");
+    if (p->dz < 0 || p->dz > GPP_MAX_DZ) ARG_FAIL("gpp_create: dz out of range");
+    if (p->dq == 0 && p->dz == 0) ARG_FAIL("gpp_create: no inputs");
+    if (p->dz > 0 && (p->n_combo <= 0 || !p->level_idx)) ARG_FAIL("gpp_create: latent map needs n_combo and level_idx");
+    if (p->n_noise < 1 || p->n_mean < 0) ARG_FAIL("gpp_create: n_noise must be >= 1 and n_mean >= 0");
+    if (p->kernel < 0 || p->kernel > 2) ARG_FAIL("gpp_create: unknown kernel");
+    if ((p->dq > 0 && !p->xq) || !p->y) ARG_FAIL("gpp_create: xq / y missing");
+    int ndev = gpp_device_count();
+    if (ndev <= 0) {
+        g_err = "gpp_create: no CUDA device visible (this engine has no CPU path)";
+        return GPP_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) ARG_FAIL("gpp_create: bad device index");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        g_err = "gpp_create: built for sm_100a (B200); device compute capability is too old";
+        return GPP_ERR_CUDA;
+    }
+
+    gpp_handle* h = new gpp_handle();
+    memset(&h->tm, 0, sizeof(h->tm));
+    for (int i = 0; i < EV_COUNT; i++) h->ev_valid[i] = false;
+    h->device = device;
+    h->n = p->n;
+    h->np = (p->n + 127) / 128 * 128;
+    h->T = (int)(h->np / 128);
+    h->dq = p->dq;
+    h->dqp = pad_dq(p->dq);
+    h->dz = p->dz;
+    h->n_combo = p->dz > 0 ? p->n_combo : 0;
+    h->n_noise = p->n_noise;
+    h->n_mean = p->n_mean;
+    h->kernel = p->kernel;
+    const long long n = h->n, np = h->np;
+    const int T = h->T;
+
+#define CKH(x)                    \
+    do {                          \
+        cudaError_t e_ = (x);     \
+        if (e_ != cudaSuccess) {  \
+            set_err(#x, e_);      \
+            gpp_destroy(h);       \
+            return GPP_ERR_CUDA;  \
+        }                         \
+    } while (0)
+
+    CKH(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+    for (int i = 0; i < EV_COUNT; i++) CKH(cudaEventCreate(&h->ev[i]));
+    CKH(chol_set_attributes());
+    CKH(cov_set_attributes());
+
+    CKH(dev_alloc(&h->xq, (size_t)n * h->dq));
+    CKH(dev_alloc(&h->y, (size_t)n));
+    CKH(dev_alloc(&h->centre, (size_t)std::max(h->dq, 1)));
+    if (h->dq > 0) CKH(cudaMemcpy(h->xq, p->xq, sizeof(double) * n * h->dq, cudaMemcpyDefault));
+    CKH(cudaMemcpy(h->y, p->y, sizeof(double) * n, cudaMemcpyDefault));
+    {
+        // column means of the training inputs (the centring of gpytorch's covar_dist)
+        std::vector<double> xh((size_t)n * std::max(h->dq, 1)), c(std::max(h->dq, 1), 0.0);
+        if (h->dq > 0) CKH(cudaMemcpy(xh.data(), h->xq, sizeof(double) * n * h->dq, cudaMemcpyDeviceToHost));
+        for (int d = 0; d < h->dq; d++) {
+            double s = 0.0;
+            for (long long i = 0; i < n; i++) s += xh[i * h->dq + d];
+            c[d] = s / (double)n;
+        }
+        CKH(cudaMemcpy(h->centre, c.data(), sizeof(double) * std::max(h->dq, 1), cudaMemcpyHostToDevice));
+    }
+    auto upload_idx = [&](const int32_t* src, int** dst, int hi, const char* name) -> int {
+        if (!src) return GPP_OK;
+        std::vector<int> tmp((size_t)n);
+        cudaError_t e = cudaMemcpy(tmp.data(), src, sizeof(int) * n, cudaMemcpyDefault);
+        if (e != cudaSuccess) {
+            set_err("index upload", e);
+            return GPP_ERR_CUDA;
+        }
+        for (long long i = 0; i < n; i++)
+            if (tmp[i] >= hi || tmp[i] < -1) {
+                g_err = std::string("gpp_create: ") + name + " out of range";
+                return GPP_ERR_ARG;
+            }
+        e = dev_alloc(dst, (size_t)n);
+        if (e == cudaSuccess) e = cudaMemcpy(*dst, tmp.data(), sizeof(int) * n, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            set_err("index upload", e);
+            return GPP_ERR_CUDA;
+        }
+        if (dst == &h->level_idx) h->level_idx_host = tmp;
+        return GPP_OK;
+    };
+    int rc;
+    if (h->dz > 0 && (rc = upload_idx(p->level_idx, &h->level_idx, h->n_combo, "level_idx")) != GPP_OK) {
+        gpp_destroy(h);
+        return rc;
+    }
+    if ((rc = upload_idx(p->noise_idx, &h->noise_idx, h->n_noise, "noise_idx")) != GPP_OK) {
+        gpp_destroy(h);
+        return rc;
+    }
+    if ((rc = upload_idx(p->mean_idx, &h->mean_idx, std::max(h->n_mean, 1), "mean_idx")) != GPP_OK) {
+        gpp_destroy(h);
+        return rc;
+    }
+
+    h->hyp_len = h->dq + h->n_combo * h->dz + h->n_noise + h->n_mean;
+    CKH(dev_alloc(&h->hyp, (size_t)h->hyp_len));
+    CKH(cudaMallocHost((void**)&h->hyp_host, sizeof(double) * std::max(h->hyp_len, 1)));
+    CKH(dev_alloc(&h->xs, (size_t)np * h->dqp));
+    CKH(dev_alloc(&h->nrm, (size_t)np));
+    CKH(dev_alloc(&h->zpt, (size_t)np * ZP));
+    CKH(dev_alloc(&h->r, (size_t)np));
+    CKH(dev_alloc(&h->diag_add, (size_t)np));
+    CKH(dev_alloc(&h->v, (size_t)np));
+    CKH(dev_alloc(&h->alpha, (size_t)np));
+    CKH(dev_alloc(&h->part, (size_t)T * np));
+    CKH(dev_alloc(&h->A, (size_t)np * np));
+    CKH(dev_alloc(&h->M, (size_t)np * np));
+    CKH(dev_alloc(&h->S, (size_t)np * np));
+    CKH(cudaMemsetAsync(h->M, 0, sizeof(double) * np * np, h->st));
+    CKH(dev_alloc(&h->logdet_part, (size_t)T));
+    CKH(dev_alloc(&h->info, 1));
+    CKH(cudaMallocHost((void**)&h->info_host, sizeof(int)));
+    CKH(dev_alloc(&h->tile_part, (size_t)T * (T + 1) / 2 * (1 + h->dqp)));
+    if (h->dz > 0) {
+        CKH(dev_alloc(&h->zpart, (size_t)T * np * ZP));
+        CKH(dev_alloc(&h->gz, (size_t)n * h->dz));
+        CKH(cudaMallocHost((void**)&h->gz_host, sizeof(double) * n * h->dz));
+    }
+    h->res_len = 4 + h->dq + h->n_noise + h->n_mean;
+    CKH(dev_alloc(&h->res, (size_t)h->res_len));
+    CKH(cudaMallocHost((void**)&h->res_host, sizeof(double) * h->res_len));
+    CKH(cudaStreamSynchronize(h->st));
+#undef CKH
+    *out = h;
+    return GPP_OK;
+}
+
+static void mark(gpp_handle* h, int which) {
+    cudaEventRecord(h->ev[which], h->st);
+    h->ev_valid[which] = true;
+}
+
+static float span(gpp_handle* h, int a, int b) {
+    if (!h->ev_valid[a] || !h->ev_valid[b]) return 0.f;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev[a], h->ev[b]) != cudaSuccess) {
+        cudaGetLastError();
+        return 0.f;
+    }
+    return ms;
+}
+
+static int check_hyper(const gpp_handle* h, const gpp_hyper* hy) {
+    if (!hy) ARG_FAIL("hyper: null");
+    if (h->dq > 0 && !hy->w) ARG_FAIL("hyper: w missing");
+    if (h->dz > 0 && !hy->z) ARG_FAIL("hyper: latent table z missing");
+    if (!hy->noise) ARG_FAIL("hyper: noise missing");
+    if (h->n_mean > 0 && !hy->beta) ARG_FAIL("hyper: beta missing");
+    return GPP_OK;
+}
+
+// upload hyper-parameters and prepare the per-point panels of the training set
+static int stage_prep(gpp_handle* h, const gpp_hyper* hy, double jitter) {
+    double* hh = h->hyp_host;
+    int o = 0;
+    for (int d = 0; d < h->dq; d++) hh[o++] = hy->w[d];
+    for (int k = 0; k < h->n_combo * h->dz; k++) hh[o++] = hy->z[k];
+    for (int k = 0; k < h->n_noise; k++) hh[o++] = hy->noise[k];
+    for (int k = 0; k < h->n_mean; k++) hh[o++] = hy->beta[k];
+    h->sf2 = hy->sigma_f2;
+    if (h->hyp_len > 0)
+        CK(cudaMemcpyAsync(h->hyp, hh, sizeof(double) * h->hyp_len, cudaMemcpyHostToDevice, h->st));
+    PrepArgs pa;
+    pa.xq = h->xq;
+    pa.level_idx = h->level_idx;
+    pa.w = hyp_w(h);
+    pa.centre = h->centre;
+    pa.ztab = hyp_z(h);
+    pa.n = (int)h->n;
+    pa.np = (int)h->np;
+    pa.dq = h->dq;
+    pa.dqp = h->dqp;
+    pa.dz = h->dz;
+    pa.n_combo = h->n_combo;
+    pa.xs = h->xs;
+    pa.nrm = h->nrm;
+    pa.zpt = h->zpt;
+    const int nb = (int)((h->np + 255) / 256);
+    prep_points_kernel<<<nb, 256, 0, h->st>>>(pa);
+    CK(cudaGetLastError());
+    prep_targets_kernel<<<nb, 256, 0, h->st>>>(h->y, h->mean_idx, hyp_beta(h), h->n_mean, h->noise_idx, hyp_noise(h),
+                                                h->n_noise, jitter, (int)h->n, (int)h->np, h->r, h->diag_add);
+    CK(cudaGetLastError());
+    return GPP_OK;
+}
+
+// K_y (lower tiles) into A, then A -> L in place, diagonal blocks of M <- L_kk^-1; returns potrf info
+static int stage_factor(gpp_handle* h, int* info_out) {
+    CK(cudaMemsetAsync(h->info, 0, sizeof(int), h->st));
+    CovArgs ca;
+    memset(&ca, 0, sizeof(ca));
+    ca.xs_r = ca.xs_c = h->xs;
+    ca.nrm_r = ca.nrm_c = h->nrm;
+    ca.zpt_r = ca.zpt_c = h->zpt;
+    ca.out = h->A;
+    ca.ld = h->np;
+    ca.n_r = ca.n_c = (int)h->n;
+    ca.tiles_r = ca.tiles_c = h->T;
+    ca.tri = 1;
+    ca.same = 1;
+    ca.pad_identity = 1;
+    ca.dqp = h->dqp;
+    ca.dz = h->dz;
+    ca.sf2 = h->sf2;
+    ca.diag_add = h->diag_add;
+    CK(launch_cov(ca, h->kernel, h->st));
+    mark(h, EV_COV);
+    CK(potrf_blocked(h->A, h->M, (int)h->np, h->T, h->logdet_part, h->info, h->st));
+    mark(h, EV_CHOL);
+    CK(cudaMemcpyAsync(h->info_host, h->info, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    *info_out = *h->info_host;
+    return GPP_OK;
+}
+
+// M <- L^-1, v = M r, alpha = M^T v
+static int stage_inverse_solve(gpp_handle* h) {
+    CK(trtri_doubling(h->A, h->M, h->S, (int)h->np, h->T, h->st));
+    mark(h, EV_TRTRI);
+    trmv_lower_kernel<<<(int)(h->np / 8), 256, 0, h->st>>>(h->M, h->np, h->r, (int)h->np, h->v);
+    CK(cudaGetLastError());
+    trmv_lower_t_part_kernel<<<h->T * (h->T + 1) / 2, 128, 0, h->st>>>(h->M, h->np, h->v, (int)h->np, h->part);
+    CK(cudaGetLastError());
+    trmv_lower_t_reduce_kernel<<<(int)((h->np + 255) / 256), 256, 0, h->st>>>(h->part, (int)h->np, h->T, h->alpha);
+    CK(cudaGetLastError());
+    mark(h, EV_SOLVE);
+    return GPP_OK;
+}
+
+static int stage_grad(gpp_handle* h) {
+    CK(lauum_full(h->M, h->S, (int)h->np, h->T, h->st));
+    mark(h, EV_LAUUM);
+    GradArgs ga;
+    memset(&ga, 0, sizeof(ga));
+    ga.xs = h->xs;
+    ga.nrm = h->nrm;
+    ga.zpt = h->zpt;
+    ga.alpha = h->alpha;
+    ga.Kinv = h->S;
+    ga.ld = h->np;
+    ga.n = (int)h->n;
+    ga.np = (int)h->np;
+    ga.T = h->T;
+    ga.dq = h->dq;
+    ga.dqp = h->dqp;
+    ga.dz = h->dz;
+    ga.sf2 = h->sf2;
+    ga.tile_part = h->tile_part;
+    ga.zpart = h->zpart;
+    CK(launch_grad(ga, h->kernel, h->st));
+    if (h->dz > 0) {
+        const int cnt = (int)(h->n * h->dz);
+        zpart_reduce_kernel<<<(cnt + 255) / 256, 256, 0, h->st>>>(h->zpart, h->T, (int)h->np, (int)h->n, h->dz, h->gz);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(h->gz_host, h->gz, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->st));
+    }
+    mark(h, EV_GRAD);
+    return GPP_OK;
+}
+
+static int stage_finish(gpp_handle* h, int want_grad) {
+    FinishArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.v = h->v;
+    fa.alpha = h->alpha;
+    fa.logdet_part = h->logdet_part;
+    fa.Kinv = h->S;
+    fa.ld = h->np;
+    fa.tile_part = h->tile_part;
+    fa.w = hyp_w(h);
+    fa.noise_idx = h->noise_idx;
+    fa.mean_idx = h->mean_idx;
+    fa.info = h->info;
+    fa.n = (int)h->n;
+    fa.np = (int)h->np;
+    fa.T = h->T;
+    fa.dq = h->dq;
+    fa.dqp = h->dqp;
+    fa.n_noise = h->n_noise;
+    fa.n_mean = h->n_mean;
+    fa.want_grad = want_grad;
+    fa.res = h->res;
+    finish_kernel<<<1, 256, 0, h->st>>>(fa);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h->res_host, h->res, sizeof(double) * h->res_len, cudaMemcpyDeviceToHost, h->st));
+    mark(h, EV_END);
+    CK(cudaStreamSynchronize(h->st));
+    return GPP_OK;
+}
+
+static const double kJitter[4] = {0.0, 1e-8, 1e-7, 1e-6};  // psd_safe_cholesky ladder
+
+// factor K_y with the jitter ladder; on success L is in A and diag blocks of M are inverted
+static int factor_with_ladder(gpp_handle* h, const gpp_hyper* hy) {
+    for (int a = 0; a < 4; a++) {
+        for (int i = 0; i < EV_COUNT; i++) h->ev_valid[i] = false;
+        mark(h, EV_START);
+        int rc = stage_prep(h, hy, kJitter[a]);
+        if (rc != GPP_OK) return rc;
+        int info = 0;
+        rc = stage_factor(h, &info);
+        if (rc != GPP_OK) return rc;
+        if (info & 2) {
+            g_err = "NaN encountered while factorising K_y";
+            return GPP_ERR_NAN;
+        }
+        if (info == 0) {
+            h->last_jitter = kJitter[a];
+            return GPP_OK;
+        }
+    }
+    g_err = "K_y not positive definite after adding jitter up to 1e-6";
+    return GPP_ERR_NOT_PD;
+}
+
+extern "C" int gpp_mll_grad(gpp_handle* h, const gpp_hyper* hy, int want_grad, gpp_mll_result* out) {
+    if (!h || !out) ARG_FAIL("gpp_mll_grad: null argument");
+    int rc = check_hyper(h, hy);
+    if (rc != GPP_OK) return rc;
+    CK(cudaSetDevice(h->device));
+    h->factorized = false;
+    rc = factor_with_ladder(h, hy);
+    if (rc != GPP_OK) return rc;
+    if ((rc = stage_inverse_solve(h)) != GPP_OK) return rc;
+    if (want_grad && (rc = stage_grad(h)) != GPP_OK) return rc;
+    if ((rc = stage_finish(h, want_grad)) != GPP_OK) return rc;
+    h->factorized = true;
+
+    const double* r = h->res_host;
+    out->quad = r[0];
+    out->logdet = r[1];
+    out->jitter = h->last_jitter;
+    out->nll = 0.5 * (r[0] + r[1] + (double)h->n * 1.8378770664093453);
+    if (!(out->nll == out->nll)) {
+        g_err = "NaN in the marginal likelihood";
+        return GPP_ERR_NAN;
+    }
+    if (want_grad) {
+        out->d_sigma_f2 = r[3];
+        if (out->d_w)
+            for (int d = 0; d < h->dq; d++) out->d_w[d] = r[4 + d];
+        if (out->d_noise)
+            for (int k = 0; k < h->n_noise; k++) out->d_noise[k] = r[4 + h->dq + k];
+        if (out->d_beta)
+            for (int k = 0; k < h->n_mean; k++) out->d_beta[k] = r[4 + h->dq + h->n_noise + k];
+        if (out->d_z && h->dz > 0) {
+            // d nll / d Z[a] = sum_{i in a} sum_j P_ij (z_i - z_j): scatter the per-point sums by level
+            for (int k = 0; k < h->n_combo * h->dz; k++) out->d_z[k] = 0.0;
+            for (long long i = 0; i < h->n; i++) {
+                int a = h->level_idx_host[(size_t)i];
+                if (a < 0) continue;
+                for (int k = 0; k < h->dz; k++) out->d_z[a * h->dz + k] += h->gz_host[i * h->dz + k];
+            }
+        }
+    } else {
+        out->d_sigma_f2 = 0.0;
+    }
+    h->tm.covariance = span(h, EV_START, EV_COV);
+    h->tm.cholesky = span(h, EV_COV, EV_CHOL);
+    h->tm.trtri = span(h, EV_CHOL, EV_TRTRI);
+    h->tm.solve = span(h, EV_TRTRI, EV_SOLVE);
+    h->tm.lauum = want_grad ? span(h, EV_SOLVE, EV_LAUUM) : 0.f;
+    h->tm.gradient = want_grad ? span(h, EV_LAUUM, EV_GRAD) : 0.f;
+    h->tm.total = span(h, EV_START, EV_END);
+    return GPP_OK;
+}
+
+extern "C" int gpp_get_timings(gpp_handle* h, gpp_timings* out) {
+    if (!h || !out) ARG_FAIL("gpp_get_timings: null argument");
+    *out = h->tm;
+    return GPP_OK;
+}
+
+extern "C" int gpp_covariance(gpp_handle* h, const gpp_hyper* hy, double* k_out) {
+    if (!h || !k_out) ARG_FAIL("gpp_covariance: null argument");
+    int rc = check_hyper(h, hy);
+    if (rc != GPP_OK) return rc;
+    CK(cudaSetDevice(h->device));
+    h->factorized = false;
+    if ((rc = stage_prep(h, hy, 0.0)) != GPP_OK) return rc;
+    CovArgs ca;
+    memset(&ca, 0, sizeof(ca));
+    ca.xs_r = ca.xs_c = h->xs;
+    ca.nrm_r = ca.nrm_c = h->nrm;
+    ca.zpt_r = ca.zpt_c = h->zpt;
+    ca.out = h->S;
+    ca.ld = h->np;
+    ca.n_r = ca.n_c = (int)h->n;
+    ca.tiles_r = ca.tiles_c = h->T;
+    ca.tri = 0;
+    ca.same = 1;
+    ca.pad_identity = 0;
+    ca.dqp = h->dqp;
+    ca.dz = h->dz;
+    ca.sf2 = h->sf2;
+    CK(launch_cov(ca, h->kernel, h->st));
+    CK(cudaMemcpy2DAsync(k_out, sizeof(double) * h->n, h->S, sizeof(double) * h->np, sizeof(double) * h->n, h->n,
+                         cudaMemcpyDefault, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    return GPP_OK;
+}
+
+extern "C" int gpp_fetch(gpp_handle* h, int which, double* out) {
+    if (!h || !out) ARG_FAIL("gpp_fetch: null argument");
+    CK(cudaSetDevice(h->device));
+    if (which == 3) {
+        CK(cudaMemcpyAsync(out, h->alpha, sizeof(double) * h->n, cudaMemcpyDefault, h->st));
+        CK(cudaStreamSynchronize(h->st));
+        return GPP_OK;
+    }
+    const double* src = which == 0 ? h->A : (which == 1 ? h->M : (which == 2 ? h->S : nullptr));
+    if (!src) ARG_FAIL("gpp_fetch: which must be 0..3");
+    std::vector<double> tmp((size_t)h->n * h->n);
+    CK(cudaMemcpy2DAsync(tmp.data(), sizeof(double) * h->n, src, sizeof(double) * h->np, sizeof(double) * h->n, h->n,
+                         cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    if (which < 2)
+        for (long long i = 0; i < h->n; i++)
+            for (long long j = i + 1; j < h->n; j++) tmp[(size_t)(i * h->n + j)] = 0.0;
+    CK(cudaMemcpy(out, tmp.data(), sizeof(double) * h->n * h->n, cudaMemcpyDefault));
+    return GPP_OK;
+}
+
+extern "C" int gpp_factorize(gpp_handle* h, const gpp_hyper* hy) {
+    if (!h) ARG_FAIL("gpp_factorize: null handle");
+    int rc = check_hyper(h, hy);
+    if (rc != GPP_OK) return rc;
+    CK(cudaSetDevice(h->device));
+    h->factorized = false;
+    rc = factor_with_ladder(h, hy);
+    if (rc != GPP_OK) return rc;
+    if ((rc = stage_inverse_solve(h)) != GPP_OK) return rc;
+    CK(cudaStreamSynchronize(h->st));
+    h->factorized = true;
+    return GPP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+static int ensure_chunk_buffers(gpp_handle* h, long long m) {
+    // K* chunk of at most 2^27 doubles (1 GiB)
+    long long cap = ((1LL << 27) / h->np) / 128 * 128;
+    if (cap < 128) cap = 128;
+    long long want = std::min((m + 127) / 128 * 128, cap);
+    if (want <= h->mc_alloc) return GPP_OK;
+    void* olds[] = {h->c_xq, h->c_xs, h->c_nrm, h->c_zpt, h->c_K, h->c_lvl, h->c_noise, h->c_mean, h->c_cost,
+                    h->c_mean_part, h->c_rowsq, h->c_mu, h->c_var, h->c_score, h->c_blk_best, h->c_blk_idx};
+    for (void* p : olds)
+        if (p) cudaFree(p);
+    h->c_xq = h->c_xs = h->c_nrm = h->c_zpt = h->c_K = nullptr;
+    h->c_lvl = h->c_noise = h->c_mean = h->c_cost = nullptr;
+    h->c_mean_part = h->c_rowsq = h->c_mu = h->c_var = h->c_score = h->c_blk_best = nullptr;
+    h->c_blk_idx = nullptr;
+    h->mc_alloc = 0;
+    const size_t mc = (size_t)want;
+    CK(dev_alloc(&h->c_xq, mc * std::max(h->dq, 1)));
+    CK(dev_alloc(&h->c_xs, mc * h->dqp));
+    CK(dev_alloc(&h->c_nrm, mc));
+    CK(dev_alloc(&h->c_zpt, mc * ZP));
+    CK(dev_alloc(&h->c_K, mc * (size_t)h->np));
+    CK(dev_alloc(&h->c_lvl, mc));
+    CK(dev_alloc(&h->c_noise, mc));
+    CK(dev_alloc(&h->c_mean, mc));
+    CK(dev_alloc(&h->c_cost, mc));
+    CK(dev_alloc(&h->c_mean_part, mc * (size_t)h->T));
+    CK(dev_alloc(&h->c_rowsq, mc * (size_t)h->T));
+    CK(dev_alloc(&h->c_mu, mc));
+    CK(dev_alloc(&h->c_var, mc));
+    CK(dev_alloc(&h->c_score, mc));
+    CK(dev_alloc(&h->c_blk_best, mc / 256 + 1));
+    CK(dev_alloc(&h->c_blk_idx, mc / 256 + 1));
+    h->mc_alloc = want;
+    return GPP_OK;
+}
+
+struct AcqSpec {
+    const int32_t* cost_idx = nullptr;
+    int n_cost = 0;
+    const double* cost = nullptr;
+    const int32_t* kind_by_cost = nullptr;
+    const double* best_f = nullptr;
+    int maximize = 1;
+    double si = 0.0, y_min = 0.0, y_std = 1.0;
+    double* scores = nullptr;
+    double best_score = -INFINITY;
+    long long best_index = -1;
+};
+
+static int predict_impl(gpp_handle* h, long long m, const double* xq, const int32_t* level_idx,
+                        const int32_t* noise_idx, const int32_t* mean_idx, int include_noise, double min_var,
+                        double* mean, double* var, AcqSpec* acq) {
+    if (!h->factorized) ARG_FAIL("predict: call gpp_factorize (or gpp_mll_grad) first");
+    if (m <= 0) return GPP_OK;
+    if (h->dq > 0 && !xq) ARG_FAIL("predict: xq missing");
+    if (h->dz > 0 && !level_idx) ARG_FAIL("predict: level_idx missing");
+    CK(cudaSetDevice(h->device));
+    int rc = ensure_chunk_buffers(h, m);
+    if (rc != GPP_OK) return rc;
+    if (acq) {
+        if (acq->n_cost <= 0 || !acq->cost || !acq->kind_by_cost || !acq->best_f) ARG_FAIL("acq: cost tables missing");
+        if (acq->n_cost > h->acq_cap) {
+            if (h->acq_par) cudaFree(h->acq_par);
+            if (h->acq_kind) cudaFree(h->acq_kind);
+            h->acq_par = nullptr;
+            h->acq_kind = nullptr;
+            CK(dev_alloc(&h->acq_par, (size_t)2 * acq->n_cost));
+            CK(dev_alloc(&h->acq_kind, (size_t)acq->n_cost));
+            h->acq_cap = acq->n_cost;
+        }
+        CK(cudaMemcpyAsync(h->acq_par, acq->cost, sizeof(double) * acq->n_cost, cudaMemcpyDefault, h->st));
+        CK(cudaMemcpyAsync(h->acq_par + acq->n_cost, acq->best_f, sizeof(double) * acq->n_cost, cudaMemcpyDefault,
+                           h->st));
+        CK(cudaMemcpyAsync(h->acq_kind, acq->kind_by_cost, sizeof(int) * acq->n_cost, cudaMemcpyDefault, h->st));
+    }
+    std::vector<double> hb;
+    std::vector<long long> hi;
+    const long long MC = h->mc_alloc;
+    for (long long base = 0; base < m; base += MC) {
+        const long long mc = std::min(MC, m - base);
+        const long long mcp = (mc + 127) / 128 * 128;
+        const int tiles_r = (int)(mcp / 128);
+        if (h->dq > 0)
+            CK(cudaMemcpyAsync(h->c_xq, xq + base * h->dq, sizeof(double) * mc * h->dq, cudaMemcpyDefault, h->st));
+        if (h->dz > 0)
+            CK(cudaMemcpyAsync(h->c_lvl, level_idx + base, sizeof(int) * mc, cudaMemcpyDefault, h->st));
+        if (noise_idx) CK(cudaMemcpyAsync(h->c_noise, noise_idx + base, sizeof(int) * mc, cudaMemcpyDefault, h->st));
+        if (mean_idx) CK(cudaMemcpyAsync(h->c_mean, mean_idx + base, sizeof(int) * mc, cudaMemcpyDefault, h->st));
+        if (acq && acq->cost_idx)
+            CK(cudaMemcpyAsync(h->c_cost, acq->cost_idx + base, sizeof(int) * mc, cudaMemcpyDefault, h->st));
+        PrepArgs pa;
+        pa.xq = h->c_xq;
+        pa.level_idx = h->dz > 0 ? h->c_lvl : nullptr;
+        pa.w = hyp_w(h);
+        pa.centre = h->centre;
+        pa.ztab = hyp_z(h);
+        pa.n = (int)mc;
+        pa.np = (int)mcp;
+        pa.dq = h->dq;
+        pa.dqp = h->dqp;
+        pa.dz = h->dz;
+        pa.n_combo = h->n_combo;
+        pa.xs = h->c_xs;
+        pa.nrm = h->c_nrm;
+        pa.zpt = h->c_zpt;
+        prep_points_kernel<<<(int)((mcp + 255) / 256), 256, 0, h->st>>>(pa);
+        CK(cudaGetLastError());
+
+        CovArgs ca;
+        memset(&ca, 0, sizeof(ca));
+        ca.xs_r = h->c_xs;
+        ca.nrm_r = h->c_nrm;
+        ca.zpt_r = h->c_zpt;
+        ca.xs_c = h->xs;
+        ca.nrm_c = h->nrm;
+        ca.zpt_c = h->zpt;
+        ca.out = h->c_K;
+        ca.ld = h->np;
+        ca.n_r = (int)mc;
+        ca.n_c = (int)h->n;
+        ca.tiles_r = tiles_r;
+        ca.tiles_c = h->T;
+        ca.dqp = h->dqp;
+        ca.dz = h->dz;
+        ca.sf2 = h->sf2;
+        ca.alpha = h->alpha;
+        ca.mean_part = h->c_mean_part;
+        ca.ld_part = MC;
+        CK(launch_cov(ca, h->kernel, h->st));
+
+        GemmOp op = gemm_default();  // V = K* L^-T, only its row sums of squares are kept
+        op.A = h->c_K;
+        op.lda = (int)h->np;
+        op.B = h->M;
+        op.ldb = (int)h->np;
+        op.C = nullptr;
+        op.ldc = 0;
+        op.tiles_m = op.tiles_m_last = tiles_r;
+        op.tiles_n = h->T;
+        op.klo_c = 0;
+        op.khi_sel = KSEL_TJ;
+        op.khi_c = 1;
+        op.epilogue = EPI_ROWSQ;
+        op.rowsq = h->c_rowsq;
+        op.rowsq_ld = (int)MC;
+        CK(launch_gemm(op, true, true, 1, h->st));
+
+        PredFinishArgs fa;
+        memset(&fa, 0, sizeof(fa));
+        fa.mean_part = h->c_mean_part;
+        fa.rowsq = h->c_rowsq;
+        fa.ldp = MC;
+        fa.tiles_c = h->T;
+        fa.m = (int)mc;
+        fa.base = base;
+        fa.sf2 = h->sf2;
+        fa.mean_idx = mean_idx ? h->c_mean : nullptr;
+        fa.beta = hyp_beta(h);
+        fa.n_mean = h->n_mean;
+        fa.noise_idx = noise_idx ? h->c_noise : nullptr;
+        fa.noise = hyp_noise(h);
+        fa.n_noise = h->n_noise;
+        fa.include_noise = include_noise;
+        fa.min_var = min_var;
+        fa.mean_out = h->c_mu;
+        fa.var_out = h->c_var;
+        const int nblk = (int)((mc + 255) / 256);
+        if (acq) {
+            fa.cost_idx = acq->cost_idx ? h->c_cost : nullptr;
+            fa.cost = h->acq_par;
+            fa.best_f = h->acq_par + acq->n_cost;
+            fa.kind_by_cost = h->acq_kind;
+            fa.n_cost = acq->n_cost;
+            fa.maximize = acq->maximize;
+            fa.si = acq->si;
+            fa.y_min = acq->y_min;
+            fa.y_std = acq->y_std;
+            fa.score_out = acq->scores ? h->c_score : nullptr;
+            fa.blk_best = h->c_blk_best;
+            fa.blk_idx = h->c_blk_idx;
+        }
+        predict_finish_kernel<<<nblk, 256, 0, h->st>>>(fa);
+        CK(cudaGetLastError());
+        if (mean) CK(cudaMemcpyAsync(mean + base, h->c_mu, sizeof(double) * mc, cudaMemcpyDefault, h->st));
+        if (var) CK(cudaMemcpyAsync(var + base, h->c_var, sizeof(double) * mc, cudaMemcpyDefault, h->st));
+        if (acq) {
+            if (acq->scores)
+                CK(cudaMemcpyAsync(acq->scores + base, h->c_score, sizeof(double) * mc, cudaMemcpyDefault, h->st));
+            hb.resize(nblk);
+            hi.resize(nblk);
+            CK(cudaMemcpyAsync(hb.data(), h->c_blk_best, sizeof(double) * nblk, cudaMemcpyDeviceToHost, h->st));
+            CK(cudaMemcpyAsync(hi.data(), h->c_blk_idx, sizeof(long long) * nblk, cudaMemcpyDeviceToHost, h->st));
+        }
+        CK(cudaStreamSynchronize(h->st));
+        if (acq) {
+            for (int b = 0; b < nblk; b++) {
+                if (acq->best_index < 0 || hb[b] > acq->best_score ||
+                    (hb[b] == acq->best_score && hi[b] < acq->best_index)) {
+                    acq->best_score = hb[b];
+                    acq->best_index = hi[b];
+                }
+            }
+        }
+    }
+    return GPP_OK;
+}
+
+extern "C" int gpp_predict(gpp_handle* h, int64_t m, const double* xq, const int32_t* level_idx,
+                           const int32_t* noise_idx, const int32_t* mean_idx, int include_noise, double min_var,
+                           double* mean, double* var) {
+    if (!h) ARG_FAIL("gpp_predict: null handle");
+    return predict_impl(h, m, xq, level_idx, noise_idx, mean_idx, include_noise, min_var, mean, var, nullptr);
+}
+
+extern "C" int gpp_acq_argmax(gpp_handle* h, int64_t m, const double* xq, const int32_t* level_idx,
+                              const int32_t* mean_idx, const int32_t* cost_idx, int32_t n_cost, const double* cost,
+                              const int32_t* kind_by_cost, const double* best_f, int maximize, double si,
+                              double y_min, double y_std, double min_var, double* scores, double* best_score,
+                              int64_t* best_index) {
+    if (!h) ARG_FAIL("gpp_acq_argmax: null handle");
+    AcqSpec a;
+    a.cost_idx = cost_idx;
+    a.n_cost = n_cost;
+    a.cost = cost;
+    a.kind_by_cost = kind_by_cost;
+    a.best_f = best_f;
+    a.maximize = maximize;
+    a.si = si;
+    a.y_min = y_min;
+    a.y_std = y_std;
+    a.scores = scores;
+    // the reference's candidate-table branch predicts with include_noise=False (BO_GP_plus.py:185-186)
+    int rc = predict_impl(h, m, xq, level_idx, nullptr, mean_idx, 0, min_var, nullptr, nullptr, &a);
+    if (rc != GPP_OK) return rc;
+    if (best_score) *best_score = a.best_score;
+    if (best_index) *best_index = a.best_index;
+    return GPP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" int gpp_probe_dgemm(int device, int m, int n, int k, int iters, float* ms_out) {
+    if (m <= 0 || n <= 0 || k <= 0 || (m % 128) || (n % 128) || (k % 128) || iters <= 0 || !ms_out)
+        ARG_FAIL("gpp_probe_dgemm: sizes must be positive multiples of 128");
+    CK(cudaSetDevice(device));
+    CK(gemm_set_attributes());
+    double *A = nullptr, *B = nullptr, *C = nullptr;
+    CK(dev_alloc(&A, (size_t)m * k));
+    CK(dev_alloc(&B, (size_t)n * k));
+    CK(dev_alloc(&C, (size_t)m * n));
+    CK(cudaMemset(A, 0, sizeof(double) * m * k));
+    CK(cudaMemset(B, 0, sizeof(double) * n * k));
+    GemmOp op = gemm_default();
+    op.A = A;
+    op.lda = k;
+    op.B = B;
+    op.ldb = k;
+    op.C = C;
+    op.ldc = n;
+    op.tiles_m = op.tiles_m_last = m / 128;
+    op.tiles_n = n / 128;
+    op.klo_c = 0;
+    op.khi_c = k / 128;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 2; i++) CK(launch_gemm(op, true, true, 1, 0));
+    CK(cudaEventRecord(e0, 0));
+    for (int i = 0; i < iters; i++) CK(launch_gemm(op, true, true, 1, 0));
+    CK(cudaEventRecord(e1, 0));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    *ms_out = ms / iters;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(A);
+    cudaFree(B);
+    cudaFree(C);
+    return GPP_OK;
+}
