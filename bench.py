@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""Benchmark of the GP+ hot path on B200: MLL + gradient evaluations per second at N=16384, D=10,
+Matern-5/2, FP64 (BASELINE.json configs[3]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n 16384]
+
+A *step* is one evaluation of the negative log marginal likelihood and its gradient w.r.t. all 13
+hyper-parameters on the full training set: fused covariance build, blocked DMMA Cholesky, triangular
+inverse, alpha / log|K|, K^-1, fused gradient reduction.  Under torchrun every rank owns one GPU and
+evaluates its own restarts (the path shards over independent restarts: weak scaling, no data-path
+collective); ``value`` is the whole-job rate.
+
+One JSON line is printed by rank 0 (see the keys at the bottom of ``main``).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "gp-plus_b200"))
+
+N_HEADLINE = 16384
+D = 10
+LOG2PI = 1.8378770664093453
+
+
+# ------------------------------------------------------------------------------------------------
+def make_workload(n):
+    """Sobol(d=10, seed=0) scaled to the wing bounds, y = wing(X) + N(0, 0.5^2), X standardised
+    per column, y min-max scaled by the model."""
+    from scipy.stats.qmc import Sobol, scale
+    from gpplus_b200.test_functions.analytical import WING_BOUNDS, wing_weight
+    X = scale(Sobol(d=D, seed=0).random(n), l_bounds=WING_BOUNDS[0], u_bounds=WING_BOUNDS[1])
+    rng = np.random.RandomState(0)
+    y = wing_weight(X) + 0.5 * rng.randn(n)
+    Xs = (X - X.mean(0)) / X.std(0)
+    return Xs, y
+
+
+def theta_points(model, count, seed=0):
+    """theta_init (all raw parameters 0) and small perturbations of it: well-conditioned, distinct every step."""
+    from gpplus_b200.optim.mll_scipy import MLLObjective
+    obj = MLLObjective(model, True, [0, 0])
+    base = obj.pack_parameters() * 0.0
+    rng = np.random.RandomState(seed)
+    return obj, [base + (0.05 * rng.randn(base.shape[0]) if k > 0 else 0.0) for k in range(count)]
+
+
+def natural_from_theta(theta):
+    """raw [noise, outputscale, omega_1..10, mean] -> natural parameters of the C ABI (Matern-5/2)."""
+    th = np.asarray(theta, dtype=np.float32).astype(np.float64)  # the reference casts theta to float32
+    return {"w": 2.0 * 10.0 ** th[2:12], "z": None, "sigma_f2": float(np.log1p(np.exp(th[1]))),
+            "noise": np.array([1e-8 + np.exp(th[0])]), "beta": th[12:13]}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for t, line in self.rows:
+            if t < t0 or t > t1 + 0.2:
+                continue
+            f = [s.strip() for s in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measure_fp64_peak(device):
+    """FP64 GEMM peak of this GPU, measured live the way MEASURED_PEAKS.json measures bf16: cuBLAS through
+    torch.matmul on 8192^3, best of 10 (MEASURED_PEAKS.json has no FP64 entry)."""
+    import torch
+    a = torch.randn(8192, 8192, dtype=torch.float64, device="cuda:%d" % device)
+    b = torch.randn(8192, 8192, dtype=torch.float64, device="cuda:%d" % device)
+    best = 1e9
+    for i in range(12):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        e1.synchronize()
+        if i >= 2:
+            best = min(best, e0.elapsed_time(e1))
+    del a, b
+    torch.cuda.empty_cache()
+    return 2.0 * 8192 ** 3 / (best * 1e-3) / 1e12
+
+
+def cpu_oracle_rate(n_sample, steps, warmup, n_target, threads=None):
+    """evals/s of the CPU oracle (the reference's torch path restated) at n_target, measured on a bounded
+    sample of the same workload (first n_sample points) and scaled by the O(N^3) cost."""
+    import torch
+    from oracle import gp_oracle as O
+    if threads:
+        torch.set_num_threads(threads)
+    X, y = make_workload(n_target)
+    X, y = X[:n_sample], y[:n_sample]
+    ys = (y - y.min()) / (y.max() - y.min())
+    p = {"n": n_sample, "dq": D, "dz": 0, "n_combo": 0, "n_noise": 1, "n_mean": 1, "kernel": O.KERNEL_MATERN52,
+         "xq": X, "y": ys, "level_idx": None, "noise_idx": None, "mean_idx": None}
+    rng = np.random.RandomState(1)
+    times = []
+    for k in range(warmup + steps):
+        h = natural_from_theta(0.05 * rng.randn(13))
+        t0 = time.time()
+        O.mll(p, h, want_grad=True)
+        if k >= warmup:
+            times.append(time.time() - t0)
+    t = sum(times) / len(times)
+    return 1.0 / (t * (n_target / n_sample) ** 3), t, torch.get_num_threads()
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference arm: the reference's own CPU torch path for this workload.  The reference cannot be
+    imported (gpytorch / botorch absent, no network), so the CPU restatement in oracle/ is timed (kind
+    "port"), with every host thread, on a bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_sample = min(args.n, 4096)
+    rate, t_step, threads = cpu_oracle_rate(n_sample, max(1, args.steps), max(0, min(args.warmup, 1)), args.n, cores)
+    line = {
+        "impl": "reference", "metric": "MLL+grad evals/sec (N=16k, fp64)", "value": rate, "unit": "evals/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 / rate, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "synthetic exact GP N=%d D=10 Matern-5/2 FP64 MLL+gradient" % args.n,
+                   "l2": "inputs larger than L2 (K is %.1f GiB)" % (8.0 * args.n ** 2 / 2 ** 30)},
+        "cpu_baseline": {"value": rate, "unit": "evals/s", "cores": threads, "kind": "port",
+                         "sample": "one oracle MLL+grad eval per step on the first %d points of the workload "
+                                   "(%.2f s each), scaled by (N/%d)^3 to N=%d" % (n_sample, t_step, n_sample, args.n)},
+        "e2e": {"value": rate, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from gpplus_b200 import _engine as E
+    from gpplus_b200.models import GP_Plus
+    from gpplus_b200.models.gpregression import set_default_device
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available() or E.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    set_default_device(local)
+
+    n = args.n
+    X, y = make_workload(n)
+    model = GP_Plus(torch.from_numpy(X), torch.from_numpy(y), dtype=torch.float64,
+                    quant_correlation_class="Matern52Kernel")
+    obj, thetas = theta_points(model, args.warmup + args.steps, seed=rank)
+    eng = model._get_engine()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm: X, y already in HBM, one gpp_mll_grad per step -------------------------------
+    hypers = [natural_from_theta(t) for t in thetas]
+    for k in range(args.warmup):
+        eng.mll_grad(hypers[k], want_grad=True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    l0 = E.launch_count()
+    t0 = time.time()
+    stage = {k: 0.0 for k in ("covariance", "cholesky", "trtri", "solve", "lauum", "gradient", "total")}
+    for k in range(args.warmup, args.warmup + args.steps):
+        out = eng.mll_grad(hypers[k], want_grad=True)
+        tm = eng.timings()  # CUDA events recorded on the engine's own stream inside the call
+        for s in stage:
+            stage[s] += tm[s]
+    barrier()
+    t1 = time.time()
+    launches = E.launch_count() - l0
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    elapsed = torch.tensor([t1 - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
+    elapsed = float(elapsed)
+    value = world * args.steps / elapsed
+    for s in stage:
+        stage[s] /= args.steps
+
+    # ---- end-to-end arm: the public API call (MLLObjective.fun), theta from host memory, result to host ----
+    for k in range(min(2, args.warmup)):
+        obj.fun(thetas[k])
+    barrier()
+    t0 = time.time()
+    for k in range(args.warmup, args.warmup + args.steps):
+        f, g = obj.fun(thetas[k])
+    barrier()
+    e2e_elapsed = torch.tensor([time.time() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_elapsed, op=dist.ReduceOp.MAX)
+    e2e_value = world * args.steps / float(e2e_elapsed)
+    h2d = 8 * (eng.dq + eng.n_combo * eng.dz + eng.n_noise + eng.n_mean)
+    d2h = 8 * (4 + eng.dq + eng.n_noise + eng.n_mean) + 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (dgemm_dmma_kernel: Cholesky trailing updates, L^-1, K^-1) --------
+    peak = measure_fp64_peak(local)
+    n3 = float(n) ** 3
+    tensor_ms = stage["cholesky"] + stage["trtri"] + stage["lauum"]
+    achieved = n3 / (tensor_ms * 1e-3) / 1e12  # N^3/3 (potrf) + N^3/3 (trtri) + N^3/3 (lauum) algorithmic flops
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "dgemm_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {
+        "bound": "tensor", "kernel": "dgemm_dmma_kernel (FP64 DMMA m8n8k4)", "achieved": achieved, "peak": peak,
+        "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+        "peak_source": "measured live: torch.matmul f64 8192^3 best of 10 (cuBLAS); MEASURED_PEAKS.json has no FP64 entry",
+        "algorithmic_flops_per_eval": n3,
+        "stages_ms": stage,
+        "stage_tflops": {"cholesky": n3 / 3 / (stage["cholesky"] * 1e-3) / 1e12,
+                         "trtri": n3 / 3 / (stage["trtri"] * 1e-3) / 1e12,
+                         "lauum": n3 / 3 / (stage["lauum"] * 1e-3) / 1e12},
+        "hbm_stage_gbs": {"covariance": 4.0 * n * (n + 1) / (stage["covariance"] * 1e-3) / 1e9,
+                          "gradient": 4.0 * n * (n + 1) / (stage["gradient"] * 1e-3) / 1e9},
+    }
+
+    # ---- CPU baseline: the oracle on this box's host cores, bounded sample -------------------------------
+    cores = os.cpu_count() or 1
+    n_sample = min(n, 4096)
+    rate, t_step, threads = cpu_oracle_rate(n_sample, 2, 1, n, cores)
+    cpu = {"value": rate, "unit": "evals/s", "cores": threads, "kind": "port",
+           "sample": "2 oracle MLL+grad evals on the first %d points of the workload (%.2f s each), scaled by "
+                     "(N/%d)^3 to N=%d" % (n_sample, t_step, n_sample, n)}
+
+    line = {
+        "metric": "MLL+grad evals/sec (N=16k, fp64)", "value": value, "unit": "evals/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "synthetic exact GP N=%d D=10 Matern-5/2 FP64 MLL+gradient" % n,
+                   "parallelism": "independent restarts, one per GPU (no data-path collective)",
+                   "l2": "inputs larger than L2: each step streams three %.1f GiB work matrices" % (8.0 * n * n / 2 ** 30),
+                   "nll_last": out["nll"]},
+        "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "MLLObjective.fun(theta) on GP_Plus (priors, raw->natural transforms, ctypes call, gradient "
+                       "chain rule on the host)"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=N_HEADLINE)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

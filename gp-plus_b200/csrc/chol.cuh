@@ -21,92 +21,208 @@
 namespace gpp {
 
 constexpr int LEAF_THREADS = 256;
-constexpr int LEAF_LDS = TILE + 1;
-constexpr int LEAF_SMEM_BYTES = (TILE * LEAF_LDS + 2 * TILE) * 8;
+constexpr int LB = 32;     // sub-block edge inside a 128x128 leaf
+constexpr int LLD = 132;   // smem leading dimension: 132 = 4 (mod 16) keeps every DMMA fragment load conflict-free
+constexpr int TLD = 36;    // per-warp scratch leading dimension (same residue)
+constexpr int LEAF_SMEM_BYTES = (TILE * LLD + TILE + 3 * LB * TLD) * 8;
 constexpr int PANEL_BLOCKS = 4;
+constexpr unsigned FULL = 0xffffffffu;
+
+// C(32x32) += A(32x32) * B(32x32) by one warp on DMMA; A(r,k) and B(k,n) are element getters.
+// acc[mi][ni][e] holds C(mi*8+g, ni*8+2t+e).
+template <class FA, class FB>
+__device__ __forceinline__ void warp_mm32(double (&acc)[4][4][2], FA getA, FB getB, int g, int t) {
+#pragma unroll
+    for (int kk = 0; kk < LB; kk += 4) {
+        double af[4], bf[4];
+#pragma unroll
+        for (int mi = 0; mi < 4; mi++) af[mi] = getA(mi * 8 + g, kk + t);
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) bf[ni] = getB(kk + t, ni * 8 + g);
+#pragma unroll
+        for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+    }
+}
+
+__device__ __forceinline__ void acc_zero(double (&acc)[4][4][2]) {
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+}
+
+// One warp factors the 32x32 diagonal sub-block at offset b (lane i owns row i in registers, pivots travel by
+// shuffle) and inverts the factor (lane c owns column c of the inverse; L is re-read from shared memory with
+// warp-uniform addresses).  On exit the lower triangle of the sub-block holds L, its strict upper triangle holds
+// (L^-1)^T and xd[b+i] = 1/L_ii.  log L_jj is accumulated as (mantissa product, exponent sum): one log per block.
+__device__ __forceinline__ void warp_potrf_inv32(double* S, double* xd, int b, int lane, int& bad, double& logacc) {
+    double mydinv = 0.0;
+    {
+        double a[LB];
+#pragma unroll
+        for (int k = 0; k < LB; k++) a[k] = (k <= lane) ? S[(b + lane) * LLD + b + k] : 0.0;
+        double mant = 1.0;
+        int esum = 0;
+#pragma unroll
+        for (int j = 0; j < LB; j++) {
+            const double d = __shfl_sync(FULL, a[j], j);
+            if (!(d > 0.0)) bad |= (d != d) ? 2 : 1;
+            const double l = sqrt(d);
+            const double inv = 1.0 / l;
+            int ex;
+            mant *= frexp(l, &ex);
+            esum += ex;
+            if (lane == j) mydinv = inv;
+            const double lij = (lane == j) ? l : ((lane > j) ? a[j] * inv : 0.0);
+            a[j] = lij;
+#pragma unroll
+            for (int k = j + 1; k < LB; k++) {
+                const double lkj = __shfl_sync(FULL, lij, k);
+                if (lane >= k) a[k] = fma(-lij, lkj, a[k]);
+            }
+        }
+        logacc += log(mant) + (double)esum * 0.6931471805599453;
+#pragma unroll
+        for (int k = 0; k < LB; k++)
+            if (k <= lane) S[(b + lane) * LLD + b + k] = a[k];
+        xd[b + lane] = mydinv;
+    }
+    __syncwarp();
+    // X = L^-1: X[i][c] = -(sum_{k=c}^{i-1} L[i][k] X[k][c]) / L[i][i]
+    double x[LB];
+#pragma unroll
+    for (int i = 0; i < LB; i++) {
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < i; k++) {
+            const double lik = S[(b + i) * LLD + b + k];
+            if (k & 1) s1 = fma(lik, x[k], s1);
+            else s0 = fma(lik, x[k], s0);
+        }
+        const double di = xd[b + i];
+        x[i] = (lane == i) ? di : ((lane < i) ? -(s0 + s1) * di : 0.0);
+    }
+#pragma unroll
+    for (int k = 0; k < LB; k++)
+        if (k > lane) S[(b + lane) * LLD + b + k] = x[k];
+}
 
 // info[0]: 0 ok, 1 = non-positive pivot, 2 = NaN pivot.  logdet_part[kb] = sum_j log L_jj of block kb.
+// Blocked (4 x 32) right-looking factorisation of the 128x128 diagonal block kb of A plus its explicit inverse
+// (written to the diagonal block of M): diagonal sub-blocks by one warp in registers, every 32^3 product
+// (TRSM through the sub-block inverse, SYRK updates, block forward substitution of the inverse) by one warp on DMMA.
 __global__ void __launch_bounds__(LEAF_THREADS, 1)
 leaf_potrf_trinv_kernel(double* A, int ld, int kb, double* M, double* logdet_part, int* info) {
     extern __shared__ __align__(16) double sm[];
-    double* S = sm;                      // [128][129]: lower = L, strict upper = (L^-1)^T
-    double* dsq = sm + TILE * LEAF_LDS;  // [128] L_jj
-    double* xd = dsq + TILE;             // [128] 1/L_jj
-    const int tid = threadIdx.x;
+    double* S = sm;                 // [128][LLD]: lower = L, strict upper = (L^-1)^T
+    double* xd = sm + TILE * LLD;   // [128] 1/L_jj
+    double* Tall = xd + TILE;       // [3][32][TLD] per-warp scratch
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
     double* Ab = A + (long long)kb * TILE * ld + (long long)kb * TILE;
     double* Mb = M + (long long)kb * TILE * ld + (long long)kb * TILE;
 
     for (int idx = tid; idx < TILE * TILE; idx += LEAF_THREADS) {
         int i = idx >> 7, j = idx & 127;
-        S[i * LEAF_LDS + j] = (j <= i) ? Ab[(long long)i * ld + j] : 0.0;
+        S[i * LLD + j] = (j <= i) ? Ab[(long long)i * ld + j] : 0.0;
     }
     __syncthreads();
 
-    // right-looking factorisation without per-column scaling:
-    //   S_ik -= S_ij * S_kj / S_jj  for j < k <= i ; column j is final after step j-1
-    const int row = tid >> 1, half = tid & 1;
     int bad = 0;
-    for (int j = 0; j < TILE - 1; j++) {
-        double d = S[j * LEAF_LDS + j];
-        if (!(d > 0.0)) bad |= (d != d) ? 2 : 1;
-        if (row > j) {
-            double lij = S[row * LEAF_LDS + j] / d;
-            for (int k = j + 1 + half; k <= row; k += 2)
-                S[row * LEAF_LDS + k] = fma(-lij, S[k * LEAF_LDS + j], S[row * LEAF_LDS + k]);
+    double logacc = 0.0;
+    double acc[4][4][2];
+    for (int q = 0; q < 4; q++) {
+        const int b = q * LB;
+        if (warp == 0) warp_potrf_inv32(S, xd, b, lane, bad, logacc);
+        __syncthreads();
+        if (warp < 3 - q) {  // TRSM: L_ib,q = A_ib,q * X_q^T
+            const int r0 = (q + 1 + warp) * LB;
+            acc_zero(acc);
+            warp_mm32(acc, [&](int r, int k) { return S[(r0 + r) * LLD + b + k]; },
+                      [&](int k, int c) { return k < c ? S[(b + k) * LLD + b + c] : (k == c ? xd[b + c] : 0.0); }, g, t);
+            __syncwarp();
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++)
+#pragma unroll
+                    for (int e = 0; e < 2; e++) S[(r0 + mi * 8 + g) * LLD + b + ni * 8 + 2 * t + e] = acc[mi][ni][e];
+        }
+        __syncthreads();
+        {   // SYRK: A_ib,jb -= L_ib,q L_jb,q^T for q < jb <= ib <= 3 (one warp per block pair)
+            const int m = 3 - q;  // remaining block rows
+            if (warp < m * (m + 1) / 2) {
+                int u = 0, w = warp;
+                while (w > u) { w -= u + 1; u++; }  // warp -> (u, w), w <= u
+                const int i0 = (q + 1 + u) * LB, j0 = (q + 1 + w) * LB;
+                acc_zero(acc);
+                warp_mm32(acc, [&](int r, int k) { return S[(i0 + r) * LLD + b + k]; },
+                          [&](int k, int c) { return S[(j0 + c) * LLD + b + k]; }, g, t);
+#pragma unroll
+                for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ni++)
+#pragma unroll
+                        for (int e = 0; e < 2; e++) {
+                            const int r = mi * 8 + g, c = ni * 8 + 2 * t + e;
+                            if (i0 != j0 || c <= r) S[(i0 + r) * LLD + j0 + c] -= acc[mi][ni][e];
+                        }
+            }
         }
         __syncthreads();
     }
-    {
-        double d = S[(TILE - 1) * LEAF_LDS + TILE - 1];
-        if (!(d > 0.0)) bad |= (d != d) ? 2 : 1;
-    }
-    if (bad && tid == 0) atomicOr(info, bad);
-
-    if (tid < TILE) {
-        double d = S[tid * LEAF_LDS + tid];
-        double r = sqrt(d);
-        dsq[tid] = r;
-        xd[tid] = 1.0 / r;
-    }
-    __syncthreads();
-    for (int idx = tid; idx < TILE * TILE; idx += LEAF_THREADS) {
-        int i = idx >> 7, j = idx & 127;
-        if (j < i) S[i * LEAF_LDS + j] *= xd[j];
-    }
-    __syncthreads();
-    if (tid < TILE) S[tid * LEAF_LDS + tid] = dsq[tid];
-    if (tid < 32) {
-        double s = 0.0;
-        for (int j = tid; j < TILE; j += 32) s += log(dsq[j]);
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (tid == 0) logdet_part[kb] = s;
-    }
-    __syncthreads();
-    // L back to the lower triangle of A
-    for (int idx = tid; idx < TILE * TILE; idx += LEAF_THREADS) {
-        int i = idx >> 7, j = idx & 127;
-        if (j <= i) Ab[(long long)i * ld + j] = S[i * LEAF_LDS + j];
+    if (tid == 0) {
+        logdet_part[kb] = logacc;
+        if (bad) atomicOr(info, bad);
     }
 
-    // X = L^-1, column c by forward substitution, two lanes per column; X[i][c] lives at S[c][i]
-    {
-        const int c = tid >> 1, h = tid & 1;
-        const unsigned pmask = 3u << ((tid & 31) & ~1);
-        const double xc = xd[c];
-        for (int i = c + 1; i < TILE; i++) {
-            double p = (h == 0) ? S[i * LEAF_LDS + c] * xc : 0.0;
-            for (int k = c + 1 + h; k < i; k += 2) p = fma(S[i * LEAF_LDS + k], S[c * LEAF_LDS + k], p);
-            p += __shfl_xor_sync(pmask, p, 1);
-            double xi = -p * xd[i];
-            if (h == 0) S[c * LEAF_LDS + i] = xi;
-            __syncwarp(pmask);
+    // off-diagonal 32-blocks of X = L^-1 by block forward substitution, one block-diagonal distance at a time:
+    //   X_ij = -X_ii * sum_{k=j}^{i-1} L_ik X_kj        (X[r][c] is stored at S[c][r])
+    for (int dist = 1; dist < 4; dist++) {
+        if (warp < 4 - dist) {
+            const int j = warp, i = warp + dist;
+            double* T = Tall + warp * LB * TLD;
+            acc_zero(acc);
+            for (int k = j; k < i; k++) {
+                if (k == j) {
+                    warp_mm32(acc, [&](int r, int kk) { return S[(i * LB + r) * LLD + k * LB + kk]; },
+                              [&](int kk, int n) {
+                                  return n < kk ? S[(j * LB + n) * LLD + j * LB + kk] : (n == kk ? xd[j * LB + kk] : 0.0);
+                              }, g, t);
+                } else {
+                    warp_mm32(acc, [&](int r, int kk) { return S[(i * LB + r) * LLD + k * LB + kk]; },
+                              [&](int kk, int n) { return S[(j * LB + n) * LLD + k * LB + kk]; }, g, t);
+                }
+            }
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++)
+#pragma unroll
+                    for (int e = 0; e < 2; e++) T[(mi * 8 + g) * TLD + ni * 8 + 2 * t + e] = acc[mi][ni][e];
+            __syncwarp();
+            acc_zero(acc);
+            warp_mm32(acc, [&](int r, int kk) {
+                          return kk < r ? S[(i * LB + kk) * LLD + i * LB + r] : (kk == r ? xd[i * LB + r] : 0.0);
+                      },
+                      [&](int kk, int n) { return T[kk * TLD + n]; }, g, t);
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++)
+#pragma unroll
+                    for (int e = 0; e < 2; e++)
+                        S[(j * LB + ni * 8 + 2 * t + e) * LLD + i * LB + mi * 8 + g] = -acc[mi][ni][e];
         }
+        __syncthreads();
     }
-    __syncthreads();
+
     for (int idx = tid; idx < TILE * TILE; idx += LEAF_THREADS) {
         int i = idx >> 7, c = idx & 127;
-        double v = (c < i) ? S[c * LEAF_LDS + i] : ((c == i) ? xd[i] : 0.0);
-        Mb[(long long)i * ld + c] = v;
+        if (c <= i) Ab[(long long)i * ld + c] = S[i * LLD + c];
+        Mb[(long long)i * ld + c] = (c < i) ? S[c * LLD + i] : ((c == i) ? xd[i] : 0.0);
     }
 }
 
@@ -131,6 +247,7 @@ inline cudaError_t potrf_blocked(double* A, double* M, int ld, int T, double* lo
         const int pend = p0 + pw;
         for (int col = p0; col < pend; col++) {
             leaf_potrf_trinv_kernel<<<1, LEAF_THREADS, LEAF_SMEM_BYTES, st>>>(A, ld, col, M, logdet_part, info);
+            count_launch();
             GPP_TRY(cudaGetLastError());
             const int below = T - col - 1;
             if (below <= 0) continue;

@@ -592,6 +592,7 @@ inline cudaError_t launch_cov(const CovArgs& a, int kind, cudaStream_t st) {
     int nt = a.tri ? a.tiles_r * (a.tiles_r + 1) / 2 : a.tiles_r * a.tiles_c;
     if (nt <= 0) return cudaSuccess;
     size_t sm = cov_smem_bytes(a.dqp);
+    count_launch();
     if (kind == KERNEL_EXPSQ) cov_tile_kernel<KERNEL_EXPSQ><<<nt, COV_THREADS, sm, st>>>(a);
     else if (kind == KERNEL_MATERN32) cov_tile_kernel<KERNEL_MATERN32><<<nt, COV_THREADS, sm, st>>>(a);
     else cov_tile_kernel<KERNEL_MATERN52><<<nt, COV_THREADS, sm, st>>>(a);
@@ -601,6 +602,7 @@ inline cudaError_t launch_cov(const CovArgs& a, int kind, cudaStream_t st) {
 inline cudaError_t launch_grad(const GradArgs& a, int kind, cudaStream_t st) {
     int nt = a.T * (a.T + 1) / 2;
     size_t sm = grad_smem_bytes(a.dqp);
+    count_launch();
     if (kind == KERNEL_EXPSQ) grad_tile_kernel<KERNEL_EXPSQ><<<nt, COV_THREADS, sm, st>>>(a);
     else if (kind == KERNEL_MATERN32) grad_tile_kernel<KERNEL_MATERN32><<<nt, COV_THREADS, sm, st>>>(a);
     else grad_tile_kernel<KERNEL_MATERN52><<<nt, COV_THREADS, sm, st>>>(a);

@@ -17,7 +17,13 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 namespace gpp {
+
+// process-wide count of kernel launches issued by this library (reported by gpp_launch_count)
+inline std::atomic<long long> g_launches{0};
+inline void count_launch(int k = 1) { g_launches.fetch_add(k, std::memory_order_relaxed); }
 
 constexpr int TILE = 128;        // output tile edge and K block
 constexpr int BK = 16;           // k-chunk staged per pipeline stage
@@ -246,6 +252,7 @@ inline cudaError_t launch_gemm(const GemmOp& op, bool a_kc, bool b_kc, int nbatc
     else nt = op.tiles_m * op.tiles_n;
     if (nt <= 0 || nbatch <= 0) return cudaSuccess;
     dim3 grid(nt, nbatch), block(GEMM_THREADS);
+    count_launch();
     if (a_kc && b_kc) dgemm_dmma_kernel<true, true><<<grid, block, GEMM_SMEM_BYTES, st>>>(op);
     else if (a_kc && !b_kc) dgemm_dmma_kernel<true, false><<<grid, block, GEMM_SMEM_BYTES, st>>>(op);
     else if (!a_kc && !b_kc) dgemm_dmma_kernel<false, false><<<grid, block, GEMM_SMEM_BYTES, st>>>(op);

@@ -107,6 +107,8 @@ extern "C" int gpp_device_count(void) {
 
 extern "C" const char* gpp_last_error(void) { return g_err.c_str(); }
 
+extern "C" long long gpp_launch_count(void) { return g_launches.load(); }
+
 template <typename Tp>
 static cudaError_t dev_alloc(Tp** p, size_t count) {
     return cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(Tp));
@@ -327,9 +329,11 @@ static int stage_prep(gpp_handle* h, const gpp_hyper* hy, double jitter) {
     const int nb = (int)((h->np + 255) / 256);
     prep_points_kernel<<<nb, 256, 0, h->st>>>(pa);
     CK(cudaGetLastError());
+    count_launch();
     prep_targets_kernel<<<nb, 256, 0, h->st>>>(h->y, h->mean_idx, hyp_beta(h), h->n_mean, h->noise_idx, hyp_noise(h),
                                                 h->n_noise, jitter, (int)h->n, (int)h->np, h->r, h->diag_add);
     CK(cudaGetLastError());
+    count_launch();
     return GPP_OK;
 }
 
@@ -368,10 +372,13 @@ static int stage_inverse_solve(gpp_handle* h) {
     mark(h, EV_TRTRI);
     trmv_lower_kernel<<<(int)(h->np / 8), 256, 0, h->st>>>(h->M, h->np, h->r, (int)h->np, h->v);
     CK(cudaGetLastError());
+    count_launch();
     trmv_lower_t_part_kernel<<<h->T * (h->T + 1) / 2, 128, 0, h->st>>>(h->M, h->np, h->v, (int)h->np, h->part);
     CK(cudaGetLastError());
+    count_launch();
     trmv_lower_t_reduce_kernel<<<(int)((h->np + 255) / 256), 256, 0, h->st>>>(h->part, (int)h->np, h->T, h->alpha);
     CK(cudaGetLastError());
+    count_launch();
     mark(h, EV_SOLVE);
     return GPP_OK;
 }
@@ -401,6 +408,7 @@ static int stage_grad(gpp_handle* h) {
         const int cnt = (int)(h->n * h->dz);
         zpart_reduce_kernel<<<(cnt + 255) / 256, 256, 0, h->st>>>(h->zpart, h->T, (int)h->np, (int)h->n, h->dz, h->gz);
         CK(cudaGetLastError());
+    count_launch();
         CK(cudaMemcpyAsync(h->gz_host, h->gz, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->st));
     }
     mark(h, EV_GRAD);
@@ -431,6 +439,7 @@ static int stage_finish(gpp_handle* h, int want_grad) {
     fa.res = h->res;
     finish_kernel<<<1, 256, 0, h->st>>>(fa);
     CK(cudaGetLastError());
+    count_launch();
     CK(cudaMemcpyAsync(h->res_host, h->res, sizeof(double) * h->res_len, cudaMemcpyDeviceToHost, h->st));
     mark(h, EV_END);
     CK(cudaStreamSynchronize(h->st));
@@ -692,6 +701,7 @@ static int predict_impl(gpp_handle* h, long long m, const double* xq, const int3
         pa.zpt = h->c_zpt;
         prep_points_kernel<<<(int)((mcp + 255) / 256), 256, 0, h->st>>>(pa);
         CK(cudaGetLastError());
+    count_launch();
 
         CovArgs ca;
         memset(&ca, 0, sizeof(ca));
@@ -768,6 +778,7 @@ static int predict_impl(gpp_handle* h, long long m, const double* xq, const int3
         }
         predict_finish_kernel<<<nblk, 256, 0, h->st>>>(fa);
         CK(cudaGetLastError());
+    count_launch();
         if (mean) CK(cudaMemcpyAsync(mean + base, h->c_mu, sizeof(double) * mc, cudaMemcpyDefault, h->st));
         if (var) CK(cudaMemcpyAsync(var + base, h->c_var, sizeof(double) * mc, cudaMemcpyDefault, h->st));
         if (acq) {

@@ -122,9 +122,14 @@ class Prior:
         return x
 
 
+def _f64(v):
+    """Prior constants are held in float64 so log-densities carry no float32 rounding of log(scale)."""
+    return torch.as_tensor(v, dtype=torch.float64) if not torch.is_tensor(v) else v.to(torch.float64)
+
+
 class NormalPrior(Prior, Normal):
     def __init__(self, loc, scale, validate_args=None):
-        Normal.__init__(self, loc=loc, scale=scale, validate_args=validate_args)
+        Normal.__init__(self, loc=_f64(loc), scale=_f64(scale), validate_args=validate_args)
 
     def expand(self, batch_shape, _instance=None):
         batch_shape = torch.Size(batch_shape)
@@ -133,7 +138,7 @@ class NormalPrior(Prior, Normal):
 
 class LogNormalPrior(Prior, LogNormal):
     def __init__(self, loc, scale, validate_args=None):
-        LogNormal.__init__(self, loc=loc, scale=scale, validate_args=validate_args)
+        LogNormal.__init__(self, loc=_f64(loc), scale=_f64(scale), validate_args=validate_args)
 
     def expand(self, batch_shape, _instance=None):
         batch_shape = torch.Size(batch_shape)

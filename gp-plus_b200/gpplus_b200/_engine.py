@@ -20,7 +20,7 @@ MAX_DQ, MAX_DZ = 32, 4
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libgpplus_b200.so")
 
 EXPORTS = (
-    "gpp_version", "gpp_device_count", "gpp_last_error", "gpp_create", "gpp_destroy", "gpp_mll_grad",
+    "gpp_version", "gpp_device_count", "gpp_last_error", "gpp_launch_count", "gpp_create", "gpp_destroy", "gpp_mll_grad",
     "gpp_get_timings", "gpp_covariance", "gpp_fetch", "gpp_factorize", "gpp_predict", "gpp_acq_argmax",
     "gpp_probe_dgemm",
 )
@@ -80,6 +80,7 @@ def load_library():
         lib.gpp_version.restype = C.c_int
         lib.gpp_device_count.restype = C.c_int
         lib.gpp_last_error.restype = C.c_char_p
+        lib.gpp_launch_count.restype = C.c_longlong
         lib.gpp_create.argtypes = [C.POINTER(_Problem), C.c_int, C.POINTER(C.c_void_p)]
         lib.gpp_create.restype = C.c_int
         lib.gpp_destroy.argtypes = [C.c_void_p]
@@ -105,6 +106,11 @@ def load_library():
         lib.gpp_probe_dgemm.restype = C.c_int
         _lib = lib
         return lib
+
+
+def launch_count() -> int:
+    """CUDA kernels launched by the library in this process so far."""
+    return int(load_library().gpp_launch_count())
 
 
 def device_count() -> int:

@@ -1,0 +1,455 @@
+"""``GP_Plus``: mixed-variable / multi-fidelity GP with a learned latent map for categorical inputs.
+
+Mirrors the hot-path surface of models/gp_plus.py of the reference: constructor arguments and
+validation (:79-182), index bookkeeping (:184-215), the kernel tree -- fixed-lengthscale RBF on the
+latent coordinates times an ARD kernel on the quantitative columns (:219-303) --, the one-hot /
+level-combination table (:1027-1073), the latent map ``FFNN`` / ``Linear_MAP`` whose weights are
+registered on the model as ``latent[...]`` with N(0,1) priors (:1227-1265, :1456-1461), the constant /
+zero / multiple-constant mean functions (:488-544), ``fit`` (:547-599) and ``predict`` (:621-628).
+
+Differences by design: there is no per-row Python work per evaluation (the level-combination index
+of every training row is computed once), and no dense matrix is ever built in Python -- the model
+hands natural hyper-parameters to ``libgpplus_b200.so``.  Research variants that are outside the
+accelerated path (probabilistic embedding, calibration, NN / polynomial means, several separate
+latent maps) raise ``NotImplementedError`` instead of silently running something else.
+"""
+from __future__ import annotations
+
+import math
+import warnings
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .. import kernels
+from .._compat import ConstantMean, MultivariateNormal, NormalPrior, Positive, ZeroMean
+from ..optim import fit_model_continuation, fit_model_scipy, fit_model_torch
+from ..preprocessing import setlevels
+from ..priors import MollifiedUniformPrior
+from ..utils import data_type_check
+from .gpregression import GPR
+
+_QUANT_CLASSES = ("Rough_RBF", "RBFKernel", "Matern32Kernel", "Matern12Kernel", "Matern52Kernel")
+
+
+def _rough_ls(x):
+    return 2.0 ** (-0.5) * torch.pow(10, -x / 2)
+
+
+def _rough_ls_inv(x):
+    return -2.0 * torch.log10(x / 2.0)
+
+
+class GP_Plus(GPR):
+    """See the reference docstring (models/gp_plus.py:45-78) for the meaning of every argument."""
+
+    # eval-mode quirk of the reference kept by default: categorical columns of prediction inputs are
+    # re-ranked with ``setlevels`` before the level lookup (models/gp_plus.py:1081-1082)
+    relevel_on_predict = True
+
+    def __init__(
+        self,
+        train_x: torch.Tensor,
+        train_y: torch.Tensor,
+        dtype=torch.float,
+        device="cpu",
+        qual_dict={},
+        multiple_noise=False,
+        lb_noise: float = 1e-8,
+        fix_noise: bool = False,
+        fix_noise_val: float = 1e-5,
+        quant_correlation_class: str = "Rough_RBF",
+        fixed_length_scale: bool = False,
+        fixed_length_scale_val=torch.tensor([1.0]),
+        encoding_type="one-hot",
+        embedding_dim: int = 2,
+        separate_embedding=[],
+        embedding_type="deterministic",
+        NN_layers_embedding: list = [],
+        m_gp="single_constant",
+        m_gp_ref="zero",
+        NN_layers_m_gp=[],
+        calibration_type="deterministic",
+        calibration_id=[],
+        mean_prior_cal=None,
+        std_prior_cal=None,
+        interval_score=False,
+        num_pass_train=1,
+        num_pass_pred=1,
+        seed_number=1,
+    ) -> None:
+        self.interval_score = interval_score
+        self.tkwargs = {"dtype": dtype, "device": torch.device(device)}
+        self.mean_prior_cal = [0 for _ in calibration_id] if mean_prior_cal is None else mean_prior_cal
+        self.std_prior_cal = [1 for _ in calibration_id] if std_prior_cal is None else std_prior_cal
+        self.fixed_length_scale_val = fixed_length_scale_val.to(dtype=dtype) if fixed_length_scale else None
+
+        train_x = data_type_check(train_x)
+        train_y = data_type_check(train_y)
+        if not isinstance(qual_dict, dict):
+            raise ValueError("qual_dict should be a dictionary.")
+        if multiple_noise not in [True, False]:
+            raise ValueError("multiple_noise should be either True or False.")
+        if not isinstance(embedding_dim, int):
+            raise ValueError("embedding_dim should be an integer.")
+        if quant_correlation_class not in _QUANT_CLASSES:
+            raise ValueError("quant_correlation_class should be 'Rough_RBF', 'RBFKernel', 'Matern32Kernel', "
+                             "'Matern12Kernel','Matern52Kernel'.")
+        if fix_noise not in [True, False]:
+            raise ValueError("fix_noise should be either True or False.")
+        if not isinstance(NN_layers_embedding, list) or not all(isinstance(i, int) for i in NN_layers_embedding):
+            raise ValueError("NN_layers_embedding should be a list of integers representing the number of neurons "
+                             "in each layer.")
+        if encoding_type != "one-hot":
+            raise ValueError("encoding_type should be 'one-hot'.")
+        if embedding_type not in ["deterministic", "probabilistic"]:
+            raise ValueError("embedding_type should be either 'deterministic' or 'probabilistic'.")
+        if not isinstance(separate_embedding, list) or not all(isinstance(i, int) for i in separate_embedding):
+            raise ValueError("separate_embedding should be a list with integers showing the number of categorical "
+                             "inputs to be considered in a separate manifold in each layer.")
+        if not isinstance(NN_layers_m_gp, list) or not all(isinstance(i, int) for i in NN_layers_m_gp):
+            raise ValueError("NN_layers_m_gp should be a list with integers representing the number of neurons in "
+                             "each layer for the mean function.")
+        if not isinstance(calibration_id, list) or not all(isinstance(i, int) for i in calibration_id):
+            raise ValueError("calibration_id should be a list where each entry shows the column number in the "
+                             "dataset that the calibration parameters are assigned to.")
+        # variants outside the accelerated hot path
+        if embedding_type == "probabilistic" or calibration_type == "probabilistic" or len(calibration_id) > 0:
+            raise NotImplementedError("probabilistic embedding / calibration are outside the B200 engine's scope")
+        if len(separate_embedding) > 0:
+            raise NotImplementedError("separate_embedding: the reference only feeds the last latent map into the "
+                                      "kernel (models/gp_plus.py:410-437); use the default shared map")
+        if quant_correlation_class == "Matern12Kernel":
+            raise RuntimeError("Matern12Kernel not an allowed kernel")  # as models/gp_plus.py:236-241
+
+        train_x = self.fill_nan_with_mean(train_x, calibration_id)
+        self.seed = seed_number
+        self.calibration_id = calibration_id
+        self.calibration_type = calibration_type
+        qual_dict_list = list(qual_dict.keys())
+        quant_index = sorted(set(range(train_x.shape[-1])).difference(qual_dict_list))
+        num_levels_per_var = list(qual_dict.values())
+        lm_columns = list(set(qual_dict_list).difference(separate_embedding))
+        qual_kernel_columns = [*separate_embedding, lm_columns] if len(lm_columns) > 0 else separate_embedding
+        train_y = train_y.reshape(-1)
+        noise_indices = list(range(0, num_levels_per_var[-1])) if multiple_noise else []
+
+        if len(qual_dict_list) == 1 and num_levels_per_var[0] < 2:
+            quant_index = quant_index + [qual_dict_list[0]]
+            qual_dict_list = []
+            embedding_dim = 0
+        if len(qual_dict_list) == 0:
+            embedding_dim = 0
+            qual_kernel_columns = []
+
+        qual_kernels = []
+        if len(qual_dict_list) > 0:
+            for i in range(len(qual_kernel_columns)):
+                qk = kernels.RBFKernel(active_dims=torch.arange(embedding_dim) + embedding_dim * i)
+                qk.initialize(lengthscale=1.0)
+                qk.raw_lengthscale.requires_grad_(False)
+                qual_kernels.append(qk)
+
+        quant_kernel = None
+        if len(quant_index) == 0:
+            correlation_kernel = qual_kernels[0]
+            for extra in qual_kernels[1:]:
+                correlation_kernel = correlation_kernel * extra
+        else:
+            dims = len(qual_kernel_columns) * embedding_dim + torch.arange(len(quant_index))
+            if quant_correlation_class == "RBFKernel":
+                quant_kernel = kernels.RBFKernel(
+                    ard_num_dims=len(quant_index), active_dims=dims,
+                    lengthscale_constraint=Positive(transform=torch.exp, inv_transform=torch.log))
+                quant_kernel.register_prior(
+                    "lengthscale_prior", MollifiedUniformPrior(math.log(0.1), math.log(10)), "raw_lengthscale")
+            else:
+                # 'Rough_RBF' is an RBFKernel with l = 2^-1/2 10^(-omega/2), i.e. exp(-sum 10^omega dx^2)
+                cls = {"Rough_RBF": kernels.RBFKernel, "Matern32Kernel": kernels.Matern32Kernel,
+                       "Matern52Kernel": kernels.Matern52Kernel}[quant_correlation_class]
+                quant_kernel = cls(ard_num_dims=len(quant_index), active_dims=dims,
+                                   lengthscale_constraint=Positive(transform=_rough_ls, inv_transform=_rough_ls_inv))
+                quant_kernel.register_prior("lengthscale_prior", NormalPrior(-3.0, 3.0), "raw_lengthscale")
+            if len(qual_dict_list) > 0:
+                temp = qual_kernels[0]
+                for extra in qual_kernels[1:]:
+                    temp = temp * extra
+                correlation_kernel = temp * quant_kernel
+            else:
+                correlation_kernel = quant_kernel
+
+        super().__init__(train_x=train_x, train_y=train_y, noise_indices=noise_indices,
+                         correlation_kernel=correlation_kernel, fix_noise=fix_noise, fix_noise_val=fix_noise_val,
+                         lb_noise=lb_noise)
+        # shortcuts into the kernel tree; object.__setattr__ keeps them out of the module registry so that
+        # named_parameters / state_dict keep the reference's names (covar_module.base_kernel.kernels.1...)
+        object.__setattr__(self, "_quant_cols", list(quant_index))
+        object.__setattr__(self, "_qual_cols", list(qual_dict_list))
+        object.__setattr__(self, "_quant", quant_kernel)
+        object.__setattr__(self, "_latent_kernel", qual_kernels[0] if qual_kernels else None)
+        self._quant_class_name = quant_correlation_class
+
+        self.register_buffer("quant_index", torch.tensor(quant_index, dtype=torch.long))
+        self.register_buffer("qual_dict_list", torch.tensor(qual_dict_list, dtype=torch.long))
+        self.qual_kernel_columns = qual_kernel_columns
+        self.num_levels_per_var = num_levels_per_var
+        self.embedding_dim = embedding_dim
+        self.encoding_type = encoding_type
+        self.embedding_type = embedding_type
+        self.perm, self.zeta, self.perm_dict, self.A_matrix = [], [], [], []
+        self.count = train_x.size()[0]
+        self.num_pass_train, self.num_pass_pred = num_pass_train, num_pass_pred
+        self._level_strides = None
+        if len(qual_kernel_columns) > 0:
+            cols = qual_kernel_columns[-1]
+            cat = [num_levels_per_var[qual_dict_list.index(k)] for k in cols]
+            zeta, perm, perm_dict = self.zeta_matrix(num_levels=cat, embedding_dim=embedding_dim)
+            self.zeta.append(zeta)
+            self.perm.append(perm)
+            self.perm_dict.append(perm_dict)
+            latent_map = FFNN(self, input_size=sum(cat), num_classes=embedding_dim, layers=NN_layers_embedding,
+                              name="latent" + str(cols)).to(dtype=dtype)
+            self.A_matrix.append(latent_map)
+            object.__setattr__(self, "_latent_map", latent_map)
+            strides = np.ones(len(cat), dtype=np.int64)
+            for k in range(len(cat) - 2, -1, -1):
+                strides[k] = strides[k + 1] * cat[k + 1]
+            self._level_strides = (np.asarray(cat, dtype=np.int64), strides)
+
+        if fixed_length_scale:
+            self.covar_module.base_kernel.raw_lengthscale.data = self.fixed_length_scale_val
+            self.covar_module.base_kernel.raw_lengthscale.requires_grad = False
+
+        self.m_gp = m_gp
+        self.m_gp_ref = m_gp_ref
+        self.num_sources = int(torch.max(train_x[:, -1]))
+        if m_gp in ("single_constant", "single_zero"):
+            self.single_m_gp_register(train_x.shape[1], m_gp_type=m_gp, wm="mean_module")
+        elif m_gp == "multiple_constant":
+            if m_gp_ref not in ("zero", "constant"):
+                raise NotImplementedError("m_gp_ref must be 'zero' or 'constant' for the device mean gather")
+            for i in range(self.num_sources + 1):
+                kind = "single_" + m_gp_ref if i == 0 else "single_constant"
+                self.single_m_gp_register(train_x.shape[1], m_gp_type=kind, wm="mean_module_" + str(i))
+        elif m_gp.startswith("single") or m_gp.startswith("multi") or m_gp == "neural_network":
+            raise NotImplementedError("mean function %r is outside the B200 engine's scope (constant, zero and "
+                                      "multiple_constant are supported)" % m_gp)
+        else:
+            raise ValueError('The "m_gp" argument must start with "multi", "single", or "neural_network".')
+        for prm in self.parameters():  # parameters follow ``dtype``; data buffers keep the dtype of train_y
+            prm.data = prm.data.to(dtype)
+
+    # ------------------------------------------------------------------------------------------
+    # engine plumbing overrides
+    def _quant_columns(self) -> List[int]:
+        return self._quant_cols
+
+    def _quant_kernel(self):
+        return self._quant
+
+    def _level_index(self, x: torch.Tensor, training: bool) -> Optional[np.ndarray]:
+        """Row of the level-combination table per point (perm_dict lookup, gp_plus.py:1085) -- vectorised
+        mixed-radix index, identical to the itertools.product order of ``zeta_matrix``."""
+        if self._level_strides is None:
+            return None
+        cols = self.qual_kernel_columns[-1]
+        cat = x[:, cols].clone().type(torch.int64)
+        if not training and self.relevel_on_predict:
+            cat = torch.as_tensor(setlevels(cat)).type(torch.int64)
+        levels, strides = self._level_strides
+        c = cat.cpu().numpy()
+        if (c < 0).any() or (c >= levels[None, :]).any():
+            raise ValueError("The categorical input (or source indices) are not defined properly. They should be "
+                             "integer values starting from zero. To solve the issue, you can use the 'setlevels' "
+                             "function, which is a preprocessing function.")
+        return (c * strides[None, :]).sum(1).astype(np.int32)
+
+    def _latent_table(self) -> Optional[torch.Tensor]:
+        if self._level_strides is None:
+            return None
+        dtype = self.covar_module.raw_outputscale.dtype
+        z = self._latent_map(self.zeta[-1].to(dtype))
+        return z / self._latent_kernel.lengthscale.reshape(-1)[0]
+
+    def _mean_layout(self):
+        if self.m_gp == "multiple_constant":
+            consts = []
+            for i in range(self.num_sources + 1):
+                mm = getattr(self, "mean_module_" + str(i))
+                if isinstance(mm, ConstantMean):
+                    consts.append(mm.constant)
+            return len(consts), consts
+        return super()._mean_layout()
+
+    def _mean_index(self, x: torch.Tensor) -> Optional[np.ndarray]:
+        if self.m_gp != "multiple_constant":
+            return None
+        src = x[:, -1].cpu().numpy().astype(np.int64)
+        if (src < 0).any() or (src > self.num_sources).any():
+            raise ValueError("source index outside the sources seen in training")
+        shift = 1 if isinstance(getattr(self, "mean_module_0"), ZeroMean) else 0
+        return (src - shift).astype(np.int32)  # -1 selects the zero mean of the reference source
+
+    # ------------------------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor) -> MultivariateNormal:
+        """Prior mean and dense covariance at x in float64 (gp_plus.py:386-484); off the hot path."""
+        from .._dense import dense_model_covariance
+        xc = x.detach().cpu()
+        mean_x = self._mean_vector(xc)
+        return MultivariateNormal(mean_x, dense_model_covariance(self, xc))
+
+    def _mean_vector(self, x):
+        with torch.no_grad():
+            n_mean, consts = self._mean_layout()
+            out = torch.zeros(x.shape[0], dtype=torch.float64)
+            if n_mean == 0:
+                return out
+            beta = torch.cat([c.reshape(-1) for c in consts]).double()
+            idx = self._mean_index(x)
+            if idx is None:
+                return out + beta[0]
+            idx = torch.as_tensor(idx, dtype=torch.long)
+            return torch.where(idx >= 0, beta[idx.clamp_min(0)], out)
+
+    def single_m_gp_register(self, size=1, m_gp_type="single_zero", wm="mean_module"):
+        if m_gp_type == "single_constant":
+            setattr(self, wm, ConstantMean(prior=NormalPrior(0.0, 1)))
+        elif m_gp_type == "single_zero":
+            setattr(self, wm, ZeroMean())
+        else:
+            raise NotImplementedError("mean function %r is outside the B200 engine's scope" % m_gp_type)
+
+    # ------------------------------------------------------------------------------------------
+    def fit(self, add_prior: bool = True, num_restarts: int = 64, theta0_list: Optional[List[np.ndarray]] = None,
+            jac: bool = True, options: Dict = {}, n_jobs: int = -1, method="L-BFGS-B", constraint=False, bounds=False,
+            regularization_parameter: List[int] = [0, 0], optim_type="scipy"):
+        print("## Learning the model's parameters has started ##")
+        if self.tkwargs["device"].type == "cuda" and optim_type != "adam_torch":
+            # the reference cannot run its scipy path on CUDA tensors and falls back to Adam
+            # (models/gp_plus.py:551-567); here the hyper-parameters always live on the host and every
+            # optimiser drives the same GPU engine, so the requested optimiser is honoured.
+            warnings.warn("device='cuda': hyper-parameters stay on the host; the GPU engine serves optim_type=%r"
+                          % optim_type)
+        if optim_type == "scipy":
+            fit_model_scipy(self, add_prior, num_restarts, theta0_list, jac, options, n_jobs, method, constraint,
+                            bounds, regularization_parameter)
+        elif optim_type == "continuation":
+            fit_model_continuation(model=self, add_prior=add_prior, num_restarts=num_restarts, criterion="NLL",
+                                   initial_noise_var=1, red_factor=math.sqrt(10), options=options, n_jobs=n_jobs,
+                                   accuracy=1e-2, method=method, constraint=constraint,
+                                   regularization_parameter=regularization_parameter, bounds=bounds)
+        elif optim_type == "adam_torch":
+            fit_model_torch(model=self, model_param_groups=None, lr_default=0.01, num_iter=100,
+                            num_restarts=num_restarts, break_steps=50)
+        else:
+            raise ValueError(
+                'Invalid optim_type. You must choose one of the following: "scipy" (default), "continuation", or '
+                '"adam_torch".')
+        print("## Learning the model's parameters is successfully finished ##")
+
+    def fill_nan_with_mean(self, train_x, cal_ID):
+        if torch.isnan(train_x).any():
+            print("There are NaN values in the data, which will be filled with column-wise mean values."
+                  if len(cal_ID) == 0 else
+                  "There are NaN values in the data, which will be estimated in calibration process")
+            col_means = torch.nanmean(train_x, dim=0)
+            nan_idx = torch.isnan(train_x)
+            train_x[nan_idx] = col_means.repeat(train_x.shape[0], 1)[nan_idx]
+        return train_x
+
+    def predict(self, Xtest, return_std=True, include_noise=True):
+        Xtest = data_type_check(Xtest)
+        with torch.no_grad():
+            return super().predict(Xtest, return_std=return_std, include_noise=include_noise)
+
+    def predict_with_grad(self, Xtest, return_std=True, include_noise=True):
+        Xtest = data_type_check(Xtest)
+        return super().predict(Xtest, return_std=return_std, include_noise=include_noise)
+
+    def noise_value(self):
+        return self.likelihood.noise_covar.noise.detach() * self.y_std ** 2
+
+    # ------------------------------------------------------------------------------------------
+    def zeta_matrix(self, num_levels, embedding_dim: int, batch_shape=torch.Size()):
+        """All level combinations (itertools.product order) and their concatenated one-hot encodings
+        (gp_plus.py:1027-1073)."""
+        if any([i == 1 for i in num_levels]):
+            raise ValueError("Categorical variable has only one level!")
+        if embedding_dim == 1:
+            raise RuntimeWarning("1D latent variables are difficult to optimize!")
+        for level in num_levels:
+            if embedding_dim > level - 0:
+                raise RuntimeWarning("The LV dimension can atmost be num_levels-1. Setting it to %s in place of %s"
+                                     % (level - 1, min(embedding_dim, level - 1)))
+        grids = torch.meshgrid(*[torch.arange(l) for l in num_levels], indexing="ij")
+        perm = torch.stack([g.reshape(-1) for g in grids], dim=1).to(torch.int64)
+        perm_dic = {str(row.tolist()): i for i, row in enumerate(perm)}
+        one_hot = torch.cat([F.one_hot(perm[:, i], num_classes=int(num_levels[i])) for i in range(perm.shape[1])],
+                            dim=1)
+        return one_hot, perm, perm_dic
+
+    def transform_categorical(self, x: torch.Tensor, perm_dict=[], zeta=[]):
+        """One-hot rows of the level combinations in x (gp_plus.py:1077-1095); kept for API parity."""
+        if x.dim() == 1:
+            x = x.reshape(-1, 1)
+        if self.training is False:
+            x = torch.as_tensor(setlevels(x))
+        try:
+            index = [perm_dict[str(row.tolist())] for row in x.type(torch.int64)]
+        except KeyError:
+            raise ValueError("The categorical input (or source indices) are not defined properly. They should be "
+                             "integer values starting from zero. To solve the issue, you can use the 'setlevels' "
+                             "function, which is a preprocessing function.")
+        return zeta[index, :]
+
+    def get_latent_space(self):
+        if len(self.qual_kernel_columns) == 0:
+            raise RuntimeError("No categorical Variable, No latent positions")
+        with torch.no_grad():
+            dtype = self.covar_module.raw_outputscale.dtype
+            return self._latent_map(self.zeta[-1].to(dtype)).detach()
+
+
+class Linear_MAP(nn.Linear):
+    """Bias-free linear latent map z = zeta A^T (gp_plus.py:1456-1461)."""
+
+    def forward(self, input, transform=lambda x: x):
+        return F.linear(input, transform(self.weight), self.bias)
+
+
+class FFNN(nn.Module):
+    """Latent map: a bias-free linear layer, or a tanh MLP when hidden ``layers`` are given.  Weights are
+    registered on the owning model (so they pack into theta first) with N(0,1) priors (gp_plus.py:1227-1265)."""
+
+    def __init__(self, owner, input_size, num_classes, layers, name):
+        super().__init__()
+        self.hidden_num = len(layers)
+        if self.hidden_num > 0:
+            self.fci = nn.Linear(input_size, layers[0], bias=False)
+            owner.register_parameter(str(name) + "fci", self.fci.weight)
+            owner.register_prior(name="latent_prior_fci", prior=NormalPrior(0.0, 1),
+                                 param_or_closure=str(name) + "fci")
+            for i in range(1, self.hidden_num):
+                setattr(self, "h" + str(i), nn.Linear(layers[i - 1], layers[i], bias=False))
+                owner.register_parameter(str(name) + "h" + str(i), getattr(self, "h" + str(i)).weight)
+                owner.register_prior(name="latent_prior" + str(i), prior=NormalPrior(0.0, 1),
+                                     param_or_closure=str(name) + "h" + str(i))
+            self.fce = nn.Linear(layers[-1], num_classes, bias=False)
+            owner.register_parameter(str(name) + "fce", self.fce.weight)
+            owner.register_prior(name="latent_prior_fce", prior=NormalPrior(0.0, 1),
+                                 param_or_closure=str(name) + "fce")
+        else:
+            self.fci = Linear_MAP(input_size, num_classes, bias=False)
+            owner.register_parameter(name, self.fci.weight)
+            owner.register_prior(name="latent_prior_" + name, prior=NormalPrior(0, 1), param_or_closure=name)
+
+    def forward(self, x, transform=lambda x: x):
+        if self.hidden_num > 0:
+            x = torch.tanh(self.fci(x))
+            for i in range(1, self.hidden_num):
+                x = torch.tanh(getattr(self, "h" + str(i))(x))
+            return self.fce(x)
+        return self.fci(x, transform)

@@ -1,0 +1,290 @@
+"""Multi-start MAP fitting with scipy optimisers over the B200 engine.
+
+Mirrors optim/mll_scipy.py of the reference: ``marginal_log_likelihood`` (:37-60), ``MLLObjective``
+(:63-127: theta packing in ``named_parameters`` order, float32 cast of theta, ``fun`` returning
+``(nll, grad)``), ``_sample_from_prior`` (:130-138), ``get_bounds`` (:149-183),
+``_fit_model_from_state`` (:187-240, numerical failures are *returned* as values) and
+``fit_model_scipy`` (:244-307, ``num_restarts + 1`` prior draws, argmin over restarts, best theta
+loaded into the model, returns ``(results, best_nll)``).
+
+What changed underneath: the objective is one ``gpp_mll_grad`` call (fused covariance build, blocked
+DMMA Cholesky, triangular inverse, fused gradient reduction) instead of a dense torch forward +
+autograd backward, and the joblib/loky process fan-out (:287-293) becomes a restart scheduler: host
+threads that each own a model copy and an engine handle, spread over the visible GPUs; under
+``torchrun`` the restart list is sharded across ranks (one GPU each) and only ``(nll, theta)`` of
+every restart is gathered (``parallel.gather_restarts``).
+"""
+from __future__ import annotations
+
+import copy
+import os
+import queue
+import threading
+from collections import OrderedDict
+from functools import reduce
+from typing import Dict, List, Optional, Tuple, Union
+
+import numpy as np
+import torch
+from scipy.optimize import Bounds, OptimizeResult, minimize
+
+from .. import _engine, parallel
+from .._compat import NanError, NotPSDError, settings as gptsettings
+from ..utils.interval_score import interval_score_function
+
+# theta is cast to this dtype on every evaluation, exactly like the reference (mll_scipy.py:32-35,97);
+# set ``tkwargs["dtype"] = torch.float64`` to keep the optimiser's iterates unrounded.
+tkwargs = {
+    "dtype": torch.float,
+    "device": torch.device("cpu"),
+}
+
+_REG_NAMES = ["fci", "h1", "h2", "h3", "h4", "h5", "h6", "h8", "h9", "h10", "h11", "h12", "fce"]
+
+
+def marginal_log_likelihood(model, add_prior: bool, regularization_parameter=[0, 0]):
+    """log p(y | X, theta) (+ log-priors, - weight penalties): a differentiable float64 torch scalar whose
+    data term and gradient come from the GPU engine."""
+    out = model.log_marginal()
+    if add_prior:
+        for _, module, prior, closure, _ in model.named_priors():
+            out = out + prior.log_prob(closure(module)).sum()
+    l1 = 0
+    l2 = 0
+    for name, param in model.named_parameters():
+        if name in _REG_NAMES or name in ["nn_model." + s + ".bias" for s in _REG_NAMES]:
+            l2 = l2 + torch.norm(param)
+            l1 = l1 + torch.sum(torch.abs(param))
+    out = out - (regularization_parameter[0] * l1 + regularization_parameter[1] * l2)
+    if getattr(model, "interval_score", False) is True:
+        # leave-in predictive intervals at the training inputs (mll_scipy.py:57-59)
+        x = model.train_inputs[0]
+        was_training = model.training
+        mean, std = model.predict(x, return_std=True, include_noise=False)
+        model.train(was_training)
+        mu = (mean - model.y_min) / model.y_std
+        sd = std / model.y_std
+        score, _ = interval_score_function(mu + 1.96 * sd, mu - 1.96 * sd, model.y_scaled)
+        return out - 0.08 * torch.abs(out) * score
+    return out
+
+
+class MLLObjective:
+    """theta <-> model parameters, and ``fun(theta) -> (nll, d nll / d theta)`` for scipy."""
+
+    def __init__(self, model, add_prior, regularization_parameter):
+        self.model = model
+        self.add_prior = add_prior
+        self.regularization_parameter = regularization_parameter
+        self.param_shapes = OrderedDict()
+        for n, p in self.model.named_parameters():
+            if p.requires_grad:
+                self.param_shapes[n] = p.size() if len(p.size()) > 0 else torch.Size([1])
+
+    def pack_parameters(self) -> np.ndarray:
+        parts = [p.cpu().data.numpy().ravel() for _, p in self.model.named_parameters() if p.requires_grad]
+        return np.concatenate(parts)
+
+    def unpack_parameters(self, x: np.ndarray) -> "OrderedDict[str, torch.Tensor]":
+        i = 0
+        named = OrderedDict()
+        for n, shape in self.param_shapes.items():
+            length = reduce(lambda a, b: a * b, shape)
+            named[n] = torch.from_numpy(np.asarray(x[i:i + length]).reshape(*shape)).to(**tkwargs)
+            i += length
+        return named
+
+    def pack_grads(self) -> np.ndarray:
+        grads = []
+        for _, p in self.model.named_parameters():
+            if p.requires_grad:
+                g = p.grad if p.grad is not None else torch.zeros_like(p)
+                grads.append(g.cpu().data.numpy().ravel())
+        return np.concatenate(grads).astype(np.float64)
+
+    def _load(self, x: np.ndarray):
+        params = dict(self.model.named_parameters())
+        with torch.no_grad():
+            for n, v in self.unpack_parameters(x).items():
+                params[n].copy_(v.reshape(params[n].shape))
+
+    def fun(self, x: np.ndarray, return_grad=True) -> Union[float, Tuple[float, np.ndarray]]:
+        self._load(x)
+        self.model.zero_grad()
+        obj = -marginal_log_likelihood(self.model, self.add_prior, self.regularization_parameter)
+        if return_grad:
+            obj.backward()
+            return obj.item(), self.pack_grads()
+        return obj.item()
+
+
+def _sample_from_prior(model) -> np.ndarray:
+    out = []
+    for _, module, prior, closure, _ in model.named_priors():
+        if not closure(module).requires_grad:
+            continue
+        out.append(prior.expand(closure(module).shape).sample().cpu().numpy().ravel())
+    return np.concatenate(out)
+
+
+def get_bounds(likobj, theta):
+    """Box bounds per parameter name (mll_scipy.py:149-183)."""
+    lo, hi = [], []
+
+    def push(a, b, count):
+        lo.extend([a] * count)
+        hi.extend([b] * count)
+
+    for name, values in likobj.unpack_parameters(theta).items():
+        k = values.numel()
+        for col in getattr(likobj.model, "qual_kernel_columns", []):
+            if name == str(col):
+                push(-3, 3, k)
+        if name == "likelihood.noise_covar.raw_noise" or name.startswith("[") or name.startswith("latent["):
+            push(-np.inf, np.inf, k)
+        if "raw_lengthscale" in name:
+            push(-10.0, 3.0, k)
+        elif name.startswith("covar_module"):
+            push(-10.0, 3.0, k)
+        elif name.startswith("mean"):
+            push(-1.5, 1.5, k)
+        elif name.startswith("Theta_") or name.startswith("encoder"):
+            push(-15, 15, k)
+        elif name.startswith("A_matrix"):
+            push(-10, 10, k)
+    return np.array(lo, dtype=float).reshape(-1), np.array(hi, dtype=float).reshape(-1)
+
+
+def _fit_model_from_state(likobj, theta0, jac, options, method="trust-constr", constraint=False, bounds=False):
+    lo, hi = get_bounds(likobj, theta0)
+    if constraint is True:
+        raise NotImplementedError("the reference's nonlinear latent constraint reads model.nn_model, which GP_Plus "
+                                  "does not define (optim/mll_scipy.py:141-147); it is not part of the engine path")
+    box = Bounds(lo, hi) if bounds is True else None
+    try:
+        with gptsettings.fast_computations(log_prob=False):
+            return minimize(fun=likobj.fun, x0=theta0, args=(True) if jac else (False), method=method, jac=jac,
+                            bounds=box, constraints=[], options=options)
+    except Exception as e:
+        if isinstance(e, (NotPSDError, NanError)):
+            return e  # unstable starting point: scored as +inf by the caller
+        raise
+
+
+_METHOD_DEFAULTS = {
+    "L-BFGS-B": {"ftol": 1e-6, "gtol": 1e-5, "maxfun": 5000, "maxiter": 2000},
+    "trust-constr": {"verbose": 1},
+    "BFGS": {"gtol": 1e-07, "norm": np.inf, "eps": 1.4901161193847656e-08, "maxiter": None, "disp": False,
+             "return_all": False, "finite_diff_rel_step": None},
+    "SLSQP": {"maxiter": 100, "ftol": 1e-06, "iprint": 1, "disp": False, "eps": 1.4901161193847656e-08,
+              "finite_diff_rel_step": None},
+    "Newton-CG": {"xtol": 1e-05, "eps": 1.4901161193847656e-08, "maxiter": None, "disp": False,
+                  "return_all": False},
+}
+
+
+def _workers_per_gpu(n_train: int) -> int:
+    env = os.environ.get("GPPLUS_WORKERS_PER_GPU")
+    if env:
+        return max(1, int(env))
+    # small problems are launch-latency bound: keep several restarts in flight per GPU
+    if n_train <= 1024:
+        return 4
+    if n_train <= 4096:
+        return 2
+    return 1
+
+
+def _run_restarts(likobj, theta0_list, indices, jac, options, method, constraint, bounds, n_jobs) -> Dict[int, object]:
+    """Run the restarts ``indices`` of ``theta0_list`` on this process's GPUs; returns {index: result}."""
+    devices = parallel.local_devices()
+    n_train = int(likobj.model.train_targets.shape[0])
+    n_workers = len(devices) * _workers_per_gpu(n_train)
+    if n_jobs is not None and n_jobs > 0:
+        n_workers = min(n_workers, n_jobs)
+    n_workers = max(1, min(n_workers, len(indices)))
+    results: Dict[int, object] = {}
+    if len(indices) == 0:
+        return results
+    work: "queue.Queue[int]" = queue.Queue()
+    for i in indices:
+        work.put(i)
+    errors: List[BaseException] = []
+    lock = threading.Lock()
+
+    def worker(slot: int):
+        from ..models.gpregression import set_default_device
+        set_default_device(devices[slot % len(devices)])
+        local = copy.deepcopy(likobj) if n_workers > 1 else likobj
+        try:
+            while True:
+                try:
+                    i = work.get_nowait()
+                except queue.Empty:
+                    break
+                res = _fit_model_from_state(local, theta0_list[i], jac, options, method, constraint, bounds)
+                with lock:
+                    results[i] = res
+        except BaseException as e:  # propagate non-numerical failures like the reference does
+            with lock:
+                errors.append(e)
+        finally:
+            if local is not likobj:
+                local.model.release_engine()
+
+    if n_workers == 1:
+        worker(0)
+    else:
+        threads = [threading.Thread(target=worker, args=(s,), daemon=True) for s in range(n_workers)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+    if errors:
+        raise errors[0]
+    return results
+
+
+def fit_model_scipy(
+    model,
+    add_prior: bool = True,
+    num_restarts: int = 1,
+    theta0_list: Optional[List[np.ndarray]] = None,
+    jac: bool = True,
+    options: Dict = {},
+    n_jobs: int = -1,
+    method="L-BFGS-B",
+    constraint=False,
+    bounds=False,
+    regularization_parameter: List[int] = [0, 0],
+) -> Tuple[List[OptimizeResult], float]:
+    if method not in _METHOD_DEFAULTS:
+        raise ValueError("Wrong method")
+    defaults = dict(_METHOD_DEFAULTS[method])
+    for key in options.keys():
+        if key not in defaults.keys():
+            raise RuntimeError("Unknown option %s!" % key)
+        defaults[key] = options[key]
+
+    _engine.load_library()  # fail loudly before any work if the CUDA extension is missing
+    likobj = MLLObjective(model, add_prior, regularization_parameter)
+
+    if theta0_list is None:
+        theta0_list = [likobj.pack_parameters()]
+        if num_restarts > -1:
+            theta0_list.extend([_sample_from_prior(model) for _ in range(num_restarts + 1)])
+            theta0_list.pop(0)
+    # every rank must optimise from the same list: rank 0's draws win
+    theta0_list = parallel.broadcast_theta_list(theta0_list)
+
+    mine = parallel.shard_indices(len(theta0_list))
+    local = _run_restarts(likobj, theta0_list, mine, jac, defaults, method, constraint, bounds, n_jobs)
+    out = parallel.gather_restarts(local, len(theta0_list), len(theta0_list[0]) if theta0_list else 0)
+
+    nlls_opt = [np.inf if isinstance(res, Exception) else res.fun for res in out]
+    best_idx = int(np.argmin(nlls_opt))
+    try:
+        likobj._load(out[best_idx].x)
+    except Exception:
+        pass
+    return out, nlls_opt[best_idx]

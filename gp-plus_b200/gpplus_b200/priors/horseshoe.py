@@ -21,7 +21,7 @@ class LogHalfHorseshoePrior(Prior, torch.distributions.Distribution):
     has_rsample = True
 
     def __init__(self, scale, lb=1e-6, validate_args=None):
-        self.scale, self.lb = broadcast_all(scale, lb)
+        self.scale, self.lb = broadcast_all(*[torch.as_tensor(v, dtype=torch.float64) for v in (scale, lb)])
         batch_shape = torch.Size() if isinstance(scale, Number) else self.scale.size()
         torch.distributions.Distribution.__init__(self, batch_shape, validate_args=validate_args)
 

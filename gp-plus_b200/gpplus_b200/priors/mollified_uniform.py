@@ -19,7 +19,8 @@ class MollifiedUniformPrior(Prior, torch.distributions.Distribution):
     has_rsample = True
 
     def __init__(self, a, b, tail_sigma=0.1):
-        self.a, self.b, self.tail_sigma = broadcast_all(a, b, tail_sigma)
+        self.a, self.b, self.tail_sigma = broadcast_all(
+            *[torch.as_tensor(v, dtype=torch.float64) for v in (a, b, tail_sigma)])
         batch_shape = torch.Size() if isinstance(a, Number) or isinstance(b, Number) else self.a.size()
         torch.distributions.Distribution.__init__(self, batch_shape, validate_args=False)
 

@@ -117,6 +117,8 @@ typedef struct gpp_timings {
 int gpp_version(void);
 int gpp_device_count(void);
 const char* gpp_last_error(void);
+/* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
+long long gpp_launch_count(void);
 
 int gpp_create(const gpp_problem* problem, int device, gpp_handle** out);
 void gpp_destroy(gpp_handle* h);

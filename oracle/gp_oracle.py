@@ -180,8 +180,8 @@ def mll(problem: Dict, hyper: Dict, want_grad: bool = True, mode: str = "expansi
     if want_grad:
         params = [w, sf2, noise] + ([z] if z is not None else []) + ([beta] if beta is not None else [])
         grads = torch.autograd.grad(nll, params, allow_unused=True)
-        gi = iter(grads)
-        out["d_w"] = next(gi).numpy().copy() if dq > 0 else np.zeros(0)
+        gi = iter([torch.zeros_like(p_) if g_ is None else g_ for g_, p_ in zip(grads, params)])
+        out["d_w"] = next(gi).numpy().copy()
         out["d_sigma_f2"] = float(next(gi))
         out["d_noise"] = next(gi).numpy().copy()
         if z is not None:

@@ -1,0 +1,222 @@
+"""Host-side mirror of the GP+ interface (no GPU needed): parameter / prior names and order, theta
+packing with the float32 cast, priors, bounds, level indexing, restart sharding over 2 gloo ranks."""
+import math
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from gpplus_b200.models import GP_Plus
+from gpplus_b200.optim.mll_scipy import MLLObjective, _sample_from_prior, fit_model_scipy, get_bounds
+from gpplus_b200.preprocessing import setlevels, standard, train_test_split_normalizeX
+from gpplus_b200.priors import LogHalfHorseshoePrior, MollifiedUniformPrior
+from gpplus_b200.test_functions import borehole, borehole_mixed_variables, multi_fidelity_wing, wing
+from gpplus_b200.utils import inv_softplus, set_seed, softplus
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _mixed_model(dtype=torch.float64, **kw):
+    set_seed(4)
+    qual_dict = {0: 5, 5: 5}
+    X, y = borehole_mixed_variables(n=400, qual_dict=qual_dict, random_state=4)
+    Xtr, Xte, ytr, yte = train_test_split_normalizeX(X, y, test_size=0.75, qual_dict=qual_dict)
+    return GP_Plus(Xtr, ytr, qual_dict=qual_dict, dtype=dtype, **kw), Xtr, ytr, Xte
+
+
+def test_parameter_and_prior_order_mixed():
+    m, Xtr, _, _ = _mixed_model()
+    names = [n for n, p in m.named_parameters() if p.requires_grad]
+    assert names == ["latent[0, 5]", "likelihood.noise_covar.raw_noise", "covar_module.raw_outputscale",
+                     "covar_module.base_kernel.kernels.1.raw_lengthscale", "mean_module.constant"]
+    frozen = [n for n, p in m.named_parameters() if not p.requires_grad]
+    assert frozen == ["covar_module.base_kernel.kernels.0.raw_lengthscale"]
+    pri = [n for n, *_ in m.named_priors()]
+    assert pri == ["latent_prior_latent[0, 5]", "likelihood.noise_prior", "covar_module.outputscale_prior",
+                   "covar_module.base_kernel.kernels.1.lengthscale_prior", "mean_module.mean_prior"]
+    obj = MLLObjective(m, True, [0, 0])
+    assert obj.pack_parameters().shape == (29,)  # 2*10 + 1 + 1 + 6 + 1
+    assert float(m.covar_module.base_kernel.kernels[0].lengthscale) == pytest.approx(1.0)
+
+
+def test_multifidelity_model_layout():
+    set_seed(4)
+    X, y = multi_fidelity_wing(n={"0": 20, "1": 30, "2": 30, "3": 30}, random_state=4)
+    Xtr, Xte, ytr, yte = train_test_split_normalizeX(X, y, test_size=0.2, qual_dict={10: 4}, stratify=X[:, -1])
+    m = GP_Plus(Xtr, ytr, qual_dict={10: 4}, multiple_noise=True, m_gp="multiple_constant", dtype=torch.float64)
+    names = [n for n, p in m.named_parameters() if p.requires_grad]
+    assert names == ["latent[10]", "likelihood.noise_covar.raw_noise", "covar_module.raw_outputscale",
+                     "covar_module.base_kernel.kernels.1.raw_lengthscale", "mean_module_1.constant",
+                     "mean_module_2.constant", "mean_module_3.constant"]
+    assert m.likelihood.noise_covar.raw_noise.shape == (4,)
+    assert MLLObjective(m, True, [0, 0]).pack_parameters().shape == (26,)  # 8 + 4 + 1 + 10 + 3
+    mi = m._mean_index(Xtr)
+    assert mi.min() == -1 and mi.max() == 2
+    assert np.array_equal(m._noise_index(Xtr), Xtr[:, -1].numpy().astype(np.int32))
+
+
+def test_borehole_model_layout_and_transforms():
+    set_seed(1245)
+    X, y = borehole(n=1000, random_state=12345)
+    Xtr, Xte, ytr, yte = train_test_split_normalizeX(X, y, test_size=0.8)
+    m = GP_Plus(Xtr, ytr, dtype=torch.float64)
+    names = [n for n, p in m.named_parameters() if p.requires_grad]
+    assert names == ["likelihood.noise_covar.raw_noise", "covar_module.raw_outputscale",
+                     "covar_module.base_kernel.raw_lengthscale", "mean_module.constant"]
+    with torch.no_grad():
+        m.covar_module.base_kernel.raw_lengthscale.fill_(0.5)
+        w, z, sf2, noise, beta = m._natural()
+    assert torch.allclose(w, torch.full((8,), 10.0 ** 0.5, dtype=torch.float64))   # Rough_RBF: w = 10^omega
+    assert float(sf2) == pytest.approx(math.log(2.0))                               # softplus(0)
+    assert float(noise) == pytest.approx(1e-8 + 1.0)                                # lb + exp(0)
+    m2 = GP_Plus(Xtr, ytr, dtype=torch.float64, quant_correlation_class="Matern52Kernel")
+    with torch.no_grad():
+        m2.covar_module.base_kernel.raw_lengthscale.fill_(0.5)
+        assert torch.allclose(m2._natural()[0], torch.full((8,), 2 * 10.0 ** 0.5, dtype=torch.float64))
+    m3 = GP_Plus(Xtr, ytr, dtype=torch.float64, quant_correlation_class="RBFKernel")
+    with torch.no_grad():
+        m3.covar_module.base_kernel.raw_lengthscale.fill_(0.5)
+        assert torch.allclose(m3._natural()[0], torch.full((8,), 0.5 * math.exp(-1.0), dtype=torch.float64))
+    assert type(next(p for n, _, p, _, _ in m3.named_priors() if "lengthscale" in n)).__name__ == \
+        "MollifiedUniformPrior"
+
+
+def test_unsupported_variants_raise_instead_of_silently_differing():
+    X = torch.randn(20, 3, dtype=torch.float64)
+    y = torch.randn(20, dtype=torch.float64)
+    with pytest.raises(NotImplementedError):
+        GP_Plus(X, y, embedding_type="probabilistic")
+    with pytest.raises(NotImplementedError):
+        GP_Plus(X, y, m_gp="single_polynomial-d2")
+    with pytest.raises(RuntimeError):
+        GP_Plus(X, y, quant_correlation_class="Matern12Kernel")
+    with pytest.raises(ValueError):
+        GP_Plus(X, y, quant_correlation_class="Cubic")
+
+
+def test_theta_is_cast_to_float32_like_the_reference():
+    m, *_ = _mixed_model()
+    obj = MLLObjective(m, True, [0, 0])
+    x = obj.pack_parameters() + 1e-9 + 0.123456789
+    obj._load(x)
+    got = obj.pack_parameters()
+    assert np.array_equal(got, x.astype(np.float32).astype(np.float64))
+
+
+def test_level_index_matches_string_lookup():
+    m, Xtr, _, _ = _mixed_model()
+    idx = m._level_index(Xtr, True)
+    want = [m.perm_dict[0][str(row.tolist())] for row in Xtr[:, [0, 5]].type(torch.int64)]
+    assert idx.tolist() == want
+    zeta = m.zeta[0]
+    assert zeta.shape == (25, 10) and int(zeta.sum()) == 50
+    assert torch.equal(m.transform_categorical(Xtr[:7, [0, 5]], m.perm_dict[0], zeta), zeta[idx[:7]])
+    bad = Xtr.clone()
+    bad[0, 0] = 7
+    with pytest.raises(ValueError):
+        m._level_index(bad, True)
+
+
+def test_sample_from_prior_is_seeded_and_ordered():
+    m, *_ = _mixed_model()
+    torch.manual_seed(0)
+    a = _sample_from_prior(m)
+    torch.manual_seed(0)
+    b = _sample_from_prior(m)
+    assert a.shape == (29,) and np.array_equal(a, b)
+    assert a[21] > 0  # LogNormal draw used as the RAW outputscale start, as in the reference
+    lo, hi = get_bounds(MLLObjective(m, True, [0, 0]), a)
+    assert lo.shape == (29,) and np.all(np.isinf(lo[:21])) and np.all(lo[21:28] == -10) and lo[28] == -1.5
+    assert np.all(hi[21:28] == 3) and hi[28] == 1.5
+
+
+def test_prior_log_densities():
+    v = torch.tensor([-6.0, -2.0], dtype=torch.float64)
+    hs = LogHalfHorseshoePrior(0.01, 1e-8)
+    want = torch.log(torch.log(1 + 3 * (0.01 / (1e-8 + torch.exp(v))) ** 2)) + v
+    assert torch.allclose(hs.log_prob(v), want, rtol=1e-14)
+    assert float(hs.expand([3]).lb[0]) == pytest.approx(1e-6)  # expand drops lb (reference quirk)
+    mu = MollifiedUniformPrior(math.log(0.1), math.log(10))
+    inside = mu.log_prob(torch.tensor([0.0, 1.0, -2.0], dtype=torch.float64))
+    assert torch.allclose(inside, inside[0].expand(3))
+    c = -math.log(1 + (math.log(10) - math.log(0.1)) / (math.sqrt(2 * math.pi) * 0.1))
+    assert float(inside[0]) == pytest.approx(c - math.log(0.1) - 0.5 * math.log(2 * math.pi), rel=1e-12)
+    out = mu.log_prob(torch.tensor([math.log(10) + 0.2], dtype=torch.float64))
+    assert float(out) == pytest.approx(float(inside[0]) - 0.5 * (0.2 / 0.1) ** 2, rel=1e-12)
+    torch.manual_seed(1)
+    s = mu.expand([1000]).sample()
+    assert s.min() >= math.log(0.1) and s.max() < math.log(10)
+    x = torch.tensor([0.3, 2.0, 30.0], dtype=torch.float64)
+    assert torch.allclose(inv_softplus(softplus(x)), x, rtol=1e-12)
+
+
+def test_preprocessing_and_generators():
+    X, y = wing(n=64, random_state=0)
+    assert X.shape == (64, 10) and y.shape == (64,)
+    Xs, mean, std = standard(torch.tensor(X.copy()), {})
+    assert torch.allclose(Xs.mean(0), torch.zeros(10, dtype=torch.float64), atol=1e-12)
+    lv = setlevels(np.array([[3.5, 1.0], [1.5, 1.0], [3.5, 2.0]]), qual_index=[0])
+    assert lv[:, 0].tolist() == [1.0, 0.0, 1.0]
+    Xb, yb = borehole(n=32, random_state=1)
+    assert np.all(yb > 0)
+
+
+def test_fit_fails_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from gpplus_b200._engine import EngineError
+    m, *_ = _mixed_model()
+    with pytest.raises(EngineError):
+        fit_model_scipy(m, num_restarts=0)
+
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, os.path.join(%(root)r, "gp-plus_b200"))
+import numpy as np, torch, torch.distributed as dist
+from scipy.optimize import OptimizeResult
+from gpplus_b200 import parallel
+from gpplus_b200._engine import NotPSDError
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=int(sys.argv[1]), world_size=2)
+rank = dist.get_rank()
+thetas = [np.full(3, float(i)) for i in range(5)] if rank == 0 else [np.zeros(3) for _ in range(5)]
+thetas = parallel.broadcast_theta_list(thetas)
+assert all(np.all(t == i) for i, t in enumerate(thetas))
+mine = parallel.shard_indices(5)
+assert mine == list(range(rank, 5, 2))
+local = {}
+for i in mine:
+    local[i] = NotPSDError("x") if i == 3 else OptimizeResult(x=thetas[i] + 0.5, fun=10.0 - i, nit=i, nfev=2 * i,
+                                                             njev=2 * i, status=0, success=True)
+out = parallel.gather_restarts(local, 5, 3)
+assert len(out) == 5 and isinstance(out[3], NotPSDError)
+funs = [np.inf if isinstance(r, Exception) else r.fun for r in out]
+assert funs == [10.0, 9.0, 8.0, np.inf, 6.0] and int(np.argmin(funs)) == 4
+assert np.all(out[4].x == 4.5) and out[2].nfev == 4
+lo, hi = parallel.shard_range(11)
+assert (lo, hi) == ((0, 6) if rank == 0 else (6, 11))
+s, i = parallel.global_argmax(1.0 if rank == 0 else 1.0, 7 if rank == 0 else 3)
+assert (s, i) == (1.0, 3)
+s, i = parallel.global_argmax(2.0 if rank == 0 else 1.5, 7 if rank == 0 else 3)
+assert (s, i) == (2.0, 7)
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_restart_and_candidate_sharding_world2_gloo(tmp_path):
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % {"root": ROOT, "port": port})
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(2)]
+    for r, pr in enumerate(procs):
+        out, _ = pr.communicate(timeout=240)
+        assert pr.returncode == 0, out.decode()
+        assert ("rank %d ok" % r) in out.decode()

@@ -1,0 +1,144 @@
+"""The drop-in Python API on the GPU: MLLObjective.fun, fit_model_scipy and predict of GP_Plus against the
+model-level CPU oracle, on the reference's example workloads (BASELINE.json configs 1-3)."""
+import numpy as np
+import pytest
+import torch
+from scipy.optimize import minimize
+
+pytestmark = pytest.mark.gpu
+
+
+def _c1():
+    from gpplus_b200.models import GP_Plus
+    from gpplus_b200.preprocessing import train_test_split_normalizeX
+    from gpplus_b200.test_functions import borehole
+    from gpplus_b200.utils import set_seed
+    set_seed(1245)
+    X, y = borehole(n=2000, random_state=12345)
+    Xtr, Xte, ytr, yte = train_test_split_normalizeX(X, y, test_size=0.9)
+    m = GP_Plus(Xtr, ytr, dtype=torch.float64)
+    return m, {"X": Xtr.numpy(), "y": ytr.numpy(), "qual_dict": {}, "kernel": "Rough_RBF"}, Xte, yte
+
+
+def _c2(kernel="Rough_RBF"):
+    from gpplus_b200.models import GP_Plus
+    from gpplus_b200.preprocessing import train_test_split_normalizeX
+    from gpplus_b200.test_functions import borehole_mixed_variables
+    from gpplus_b200.utils import set_seed
+    set_seed(4)
+    qd = {0: 5, 5: 5}
+    X, y = borehole_mixed_variables(n=2000, qual_dict=qd, random_state=4)
+    Xtr, Xte, ytr, yte = train_test_split_normalizeX(X, y, test_size=0.75, qual_dict=qd)
+    m = GP_Plus(Xtr, ytr, qual_dict=qd, dtype=torch.float64, quant_correlation_class=kernel)
+    return m, {"X": Xtr.numpy(), "y": ytr.numpy(), "qual_dict": qd, "kernel": kernel}, Xte, yte
+
+
+def _c3():
+    from gpplus_b200.models import GP_Plus
+    from gpplus_b200.preprocessing import train_test_split_normalizeX
+    from gpplus_b200.test_functions import multi_fidelity_wing
+    from gpplus_b200.utils import set_seed
+    set_seed(4)
+    X, y = multi_fidelity_wing(n={"0": 150, "1": 300, "2": 300, "3": 300}, random_state=4)
+    qd = {10: 4}
+    Xtr, Xte, ytr, yte = train_test_split_normalizeX(X, y, test_size=0.05, qual_dict=qd, stratify=X[:, -1])
+    m = GP_Plus(Xtr, ytr, qual_dict=qd, multiple_noise=True, m_gp="multiple_constant", dtype=torch.float64)
+    spec = {"X": Xtr.numpy(), "y": ytr.numpy(), "qual_dict": qd, "kernel": "Rough_RBF", "multiple_noise": True,
+            "m_gp": "multiple_constant"}
+    return m, spec, Xte, yte
+
+
+@pytest.mark.parametrize("maker", [_c1, _c2, lambda: _c2("Matern52Kernel"), _c3])
+def test_objective_matches_oracle(maker):
+    from gpplus_b200.optim.mll_scipy import MLLObjective, _sample_from_prior
+    from oracle import gpplus_oracle as GO
+    m, spec, _, _ = maker()
+    obj = MLLObjective(m, True, [0, 0])
+    torch.manual_seed(0)
+    thetas = [obj.pack_parameters()] + [_sample_from_prior(m) for _ in range(2)]
+    for th in thetas:
+        th = np.clip(th, -6, 4)
+        f_ref, g_ref = GO.neg_log_posterior(spec, th)
+        f, g = obj.fun(th)
+        assert abs(f - f_ref) <= 1e-9 * abs(f_ref)
+        assert np.max(np.abs(g - g_ref)) <= 1e-7 * max(1.0, np.max(np.abs(g_ref)))
+        assert obj.fun(th, False) == f
+    # after fun() the model holds theta cast through float32 (side-effect contract, mll_scipy.py:115-117)
+    assert np.array_equal(obj.pack_parameters(), th.astype(np.float32).astype(np.float64))
+
+
+def test_fit_matches_cpu_oracle_fit_from_same_starts():
+    from gpplus_b200.optim.mll_scipy import MLLObjective, _sample_from_prior, fit_model_scipy
+    from oracle import gpplus_oracle as GO
+    m, spec, Xte, yte = _c1()
+    torch.manual_seed(3)
+    starts = [_sample_from_prior(m) for _ in range(4)]
+    out, best = fit_model_scipy(m, theta0_list=[s.copy() for s in starts], bounds=True)
+    assert len(out) == 4 and best == min(r.fun for r in out)
+    opts = {"ftol": 1e-6, "gtol": 1e-5, "maxfun": 5000, "maxiter": 2000}
+    from scipy.optimize import Bounds
+    from gpplus_b200.optim.mll_scipy import get_bounds
+    lo, hi = get_bounds(MLLObjective(m, True, [0, 0]), starts[0])
+    cpu = [minimize(lambda t: GO.neg_log_posterior(spec, t), s, jac=True, method="L-BFGS-B", bounds=Bounds(lo, hi),
+                    options=opts) for s in starts]
+    # same optimiser, same starts, objective equal to ~1e-12: the trajectories coincide to optimiser tolerance
+    for a, b in zip(out, cpu):
+        assert abs(a.fun - b.fun) <= 1e-4 * max(1.0, abs(b.fun))
+    # best theta is loaded into the model; predictions are sane on held-out points
+    mean, std = m.predict(Xte[:500], return_std=True)
+    rrmse = float(torch.sqrt(torch.mean((mean - yte[:500]) ** 2)) / torch.std(yte[:500]))
+    assert rrmse < 0.2 and bool(torch.all(std > 0))
+
+
+def test_predict_matches_oracle_mixed_multifidelity():
+    from oracle import gp_oracle as O
+    m, spec, Xte, yte = _c3()
+    with torch.no_grad():
+        m.covar_module.base_kernel.kernels[1].raw_lengthscale.fill_(-0.7)
+        m.likelihood.noise_covar.raw_noise.copy_(torch.tensor([-6.0, -5.0, -4.0, -7.0], dtype=torch.float64))
+        getattr(m, "latent[10]").copy_(torch.tensor([[0.0, 0.4, -0.3, 0.8], [0.0, -0.5, 0.6, 0.2]],
+                                                      dtype=torch.float64))
+        m.mean_module_2.constant.fill_(0.1)
+    Xq = Xte[:40]
+    mean, std = m.predict(Xq, return_std=True, include_noise=True)
+    Xtr = m.train_inputs[0]
+    w, z, sf2, noise, beta = [t.detach().numpy() for t in m._natural()]
+    # prediction inputs contain all four sources, so the eval-mode re-levelling is the identity here
+    assert sorted(set(Xq[:, -1].tolist())) == [0.0, 1.0, 2.0, 3.0]
+    p = {"n": Xtr.shape[0], "dq": 10, "dz": 2, "n_combo": 4, "n_noise": 4, "n_mean": 3, "kernel": 0,
+         "xq": Xtr[:, :10].numpy(), "y": m.train_targets.numpy(), "level_idx": Xtr[:, -1].numpy().astype(int),
+         "noise_idx": Xtr[:, -1].numpy().astype(int), "mean_idx": Xtr[:, -1].numpy().astype(int) - 1}
+    h = {"w": w, "z": z, "sigma_f2": float(sf2), "noise": noise, "beta": beta}
+    c = {"m": 40, "xq": Xq[:, :10].numpy(), "level_idx": Xq[:, -1].numpy().astype(int),
+         "noise_idx": Xq[:, -1].numpy().astype(int), "mean_idx": Xq[:, -1].numpy().astype(int) - 1}
+    mu, var = O.predict(p, h, c, include_noise=True)
+    y_min, y_std = float(m.y_min), float(m.y_std)
+    assert np.max(np.abs(mean.numpy() - (y_min + y_std * mu))) < 1e-8 * max(1.0, abs(y_min) + y_std)
+    assert np.max(np.abs(std.numpy() - np.sqrt(var) * y_std)) < 1e-8 * y_std
+    mean2 = m.predict(Xq, return_std=False)
+    assert torch.equal(mean, mean2)
+
+
+def test_full_fit_config2_runs_and_improves():
+    from gpplus_b200.optim.mll_scipy import MLLObjective
+    m, spec, Xte, yte = _c2()
+    obj = MLLObjective(m, True, [0, 0])
+    f0 = obj.fun(obj.pack_parameters(), False)
+    torch.manual_seed(0)
+    m.fit(num_restarts=8, bounds=True)
+    f1 = obj.fun(obj.pack_parameters(), False)
+    assert f1 < f0
+    mean = m.predict(Xte[:300], return_std=False)
+    assert torch.isfinite(mean).all()
+
+
+def test_adam_and_continuation_paths_drive_the_same_engine():
+    from gpplus_b200.optim import fit_model_continuation, fit_model_torch
+    m, spec, _, _ = _c1()
+    f, hist = fit_model_torch(m, num_iter=15, num_restarts=0)
+    assert np.isfinite(f) and hist[0][-1] < hist[0][0]
+    m2, *_ = _c1()
+    torch.manual_seed(1)
+    nll, history = fit_model_continuation(m2, num_restarts=1, bounds=True)
+    assert np.isfinite(nll) and len(history["noise_history"]) >= 1
+    assert not m2.likelihood.raw_noise.requires_grad
