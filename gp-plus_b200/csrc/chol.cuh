@@ -16,6 +16,8 @@
 //      a level is independent, so a level is two batched GEMM launches (ceil(log2 T) levels).
 //   3. lauum: K^-1 = M^T M, one launch over the lower tiles, mirrored into the upper triangle.
 #pragma once
+#include <vector>
+
 #include "dgemm_dmma.cuh"
 
 namespace gpp {
@@ -226,11 +228,328 @@ leaf_potrf_trinv_kernel(double* A, int ld, int kb, double* M, double* logdet_par
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Leaf, second generation.  Same contract as leaf_potrf_trinv_kernel (A_kk -> L_kk in place, M_kk <- L_kk^-1,
+// logdet_part[kb], info) with a much shorter critical path:
+//   * the 32x32 diagonal factorisation broadcasts each finished column through shared memory (one 16-byte
+//     uniform load feeds two updates) instead of two shuffles per update, and uses rsqrt + one Newton step
+//     instead of sqrt followed by a division;
+//   * the rows below a diagonal sub-block are solved by substitution, one lane per row, straight from the
+//     transposed factor, so they do not wait for the sub-block inverse;
+//   * the sub-block inverses are computed by a dedicated warp (named barriers 2..5) while warps 0-6 continue
+//     with the factorisation (named barrier 1); the diagonal update that gates the next sub-block is done by
+//     the factorising warp itself, so only two CTA-wide (224-thread) barriers remain per sub-block;
+//   * the off-diagonal 32-blocks of the inverse are assembled in four rounds (T = X_ii L_ik first, then the
+//     block columns in parallel) instead of nine dependent 32^3 products.
+constexpr int LTLD = 34;                               // transposed-factor row stride (even: 16-byte rows)
+constexpr int L2_S = TILE * LLD;                       // S      [128][LLD]
+constexpr int L2_XD = TILE;                            // xd     [128]  1/L_jj
+constexpr int L2_X = 4 * LB * TLD;                     // Xd     [4][32][TLD] diagonal sub-block inverses (row-major)
+constexpr int L2_T = 6 * LB * TLD;                     // T      [6][32][TLD]; aliases LT [4][32][LTLD] while factorising
+constexpr int LEAF2_SMEM_BYTES = (L2_S + L2_XD + L2_X + L2_T) * 8;
+static_assert(4 * LB * LTLD <= L2_T, "LT must fit in the T region");
+static_assert(LEAF2_SMEM_BYTES <= 232448, "leaf v2 shared memory exceeds the 227 KB per-CTA limit");
+
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+// One warp: in-register right-looking Cholesky of the 32x32 block at (b,b) of S.  Lane i owns row i.
+// Writes L (row-major) back to S, L^T to LT (LT[j][i] = L_ij) and 1/L_jj to xd.
+__device__ __forceinline__ void warp_potrf32_v2(double* S, double* xd, double* LT, int b, int lane, int& bad,
+                                                double& mant, int& esum) {
+    double a[LB];
+    double* row = S + (b + lane) * LLD + b;
+#pragma unroll
+    for (int k = 0; k < LB; k += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(row + k);
+        a[k] = (k <= lane) ? v.x : 0.0;
+        a[k + 1] = (k + 1 <= lane) ? v.y : 0.0;
+    }
+    double mydinv = 0.0;
+#pragma unroll
+    for (int j = 0; j < LB; j++) {
+        const double d = __shfl_sync(FULL, a[j], j);
+        if (!(d > 0.0)) bad |= (d != d) ? 2 : 1;
+        double rs = rsqrt(d);
+        double l = d * rs;
+        l = fma(fma(-l, l, d), 0.5 * rs, l);   // sqrt(d), one Newton step on top of d * rsqrt(d)
+        rs = fma(fma(-l, rs, 1.0), rs, rs);    // 1 / l
+        int ex;
+        mant *= frexp(l, &ex);
+        esum += ex;
+        if (lane == j) mydinv = rs;
+        const double lij = (lane == j) ? l : ((lane > j) ? a[j] * rs : 0.0);
+        a[j] = lij;
+        LT[j * LTLD + lane] = lij;
+        __syncwarp();
+#pragma unroll
+        for (int k = (j + 1) & ~1; k < LB; k += 2) {
+            const double2 lk = *reinterpret_cast<const double2*>(LT + j * LTLD + k);
+            if (k > j) a[k] = (lane >= k) ? fma(-lij, lk.x, a[k]) : a[k];
+            a[k + 1] = (lane >= k + 1) ? fma(-lij, lk.y, a[k + 1]) : a[k + 1];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < LB; k += 2) {
+        if (k <= lane) {
+            double2 v;
+            v.x = a[k];
+            v.y = (k + 1 <= lane) ? a[k + 1] : 0.0;
+            *reinterpret_cast<double2*>(row + k) = v;
+        }
+    }
+    xd[b + lane] = mydinv;
+}
+
+// One warp: rows row0..row0+31 of the block column b: x <- x * L_bb^-T by substitution (lane = row).
+__device__ __forceinline__ void warp_trsm_sub32(double* S, const double* xd, const double* LT, int row0, int b,
+                                                int lane) {
+    double x[LB];
+    double* row = S + (row0 + lane) * LLD + b;
+#pragma unroll
+    for (int k = 0; k < LB; k += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(row + k);
+        x[k] = v.x;
+        x[k + 1] = v.y;
+    }
+#pragma unroll
+    for (int j = 0; j < LB; j++) {
+        x[j] *= xd[b + j];
+        const double xj = x[j];
+#pragma unroll
+        for (int k = (j + 1) & ~1; k < LB; k += 2) {
+            const double2 lk = *reinterpret_cast<const double2*>(LT + j * LTLD + k);
+            if (k > j) x[k] = fma(-xj, lk.x, x[k]);
+            x[k + 1] = fma(-xj, lk.y, x[k + 1]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < LB; k += 2) {
+        double2 v;
+        v.x = x[k];
+        v.y = x[k + 1];
+        *reinterpret_cast<double2*>(row + k) = v;
+    }
+}
+
+// One warp: X = L_bb^-1 (lane c owns column c), written row-major to Xd[32][TLD] (zeros above the diagonal).
+__device__ __forceinline__ void warp_trinv32_v2(const double* S, const double* xd, double* Xd, int b, int lane) {
+    double x[LB];
+#pragma unroll
+    for (int i = 0; i < LB; i++) {
+        double s0 = 0.0, s1 = 0.0;
+        const double* Li = S + (b + i) * LLD + b;
+#pragma unroll
+        for (int k = 0; k + 1 < i; k += 2) {
+            const double2 l2 = *reinterpret_cast<const double2*>(Li + k);
+            s0 = fma(l2.x, x[k], s0);
+            s1 = fma(l2.y, x[k + 1], s1);
+        }
+        if (i & 1) s0 = fma(Li[i - 1], x[i - 1], s0);
+        const double di = xd[b + i];
+        x[i] = (lane == i) ? di : ((lane < i) ? -(s0 + s1) * di : 0.0);
+        Xd[i * TLD + lane] = x[i];
+    }
+}
+
+__device__ __forceinline__ void acc_store32(double* dst, int ldd, const double (&acc)[4][4][2], double sgn, int g,
+                                            int t) {
+#pragma unroll
+    for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) {
+            double2 v;
+            v.x = sgn * acc[mi][ni][0];
+            v.y = sgn * acc[mi][ni][1];
+            *reinterpret_cast<double2*>(dst + (mi * 8 + g) * ldd + ni * 8 + 2 * t) = v;
+        }
+}
+
+// prof (optional): clock64 stamps written by thread 0 / lane 0 of the inverse warp
+__global__ void __launch_bounds__(LEAF_THREADS, 1)
+leaf_potrf_trinv_v2_kernel(double* A, int ld, int kb, double* M, double* logdet_part, int* info, long long* prof) {
+    extern __shared__ __align__(16) double sm[];
+    double* S = sm;
+    double* xd = S + L2_S;
+    double* Xd = xd + L2_XD;
+    double* Tr = Xd + L2_X;
+    double* LT = Tr;  // alias: only used while factorising
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    double* Ab = A + (long long)kb * TILE * ld + (long long)kb * TILE;
+    double* Mb = M + (long long)kb * TILE * ld + (long long)kb * TILE;
+#define GPP_STAMP(i) \
+    if (prof && tid == 0) prof[i] = clock64();
+
+    GPP_STAMP(0)
+    // whole rows with 16-byte loads (the strict upper part is never read by the factorisation)
+    for (int idx = tid; idx < TILE * (TILE / 2); idx += LEAF_THREADS) {
+        const int i = idx >> 6, j2 = (idx & 63) * 2;
+        if (j2 <= i)
+            *reinterpret_cast<double2*>(S + i * LLD + j2) = *reinterpret_cast<const double2*>(Ab + (long long)i * ld + j2);
+    }
+    __syncthreads();
+    GPP_STAMP(1)
+
+    double acc[4][4][2];
+    if (warp == 7) {
+        // inverse warp: X_qq as soon as L_qq is final
+        for (int q = 0; q < 4; q++) {
+            named_bar_sync(2 + q, 64);
+            warp_trinv32_v2(S, xd, Xd + q * LB * TLD, q * LB, lane);
+        }
+        if (prof && lane == 0) prof[15] = clock64();
+    } else {
+        int bad = 0, esum = 0;
+        double mant = 1.0;
+        for (int q = 0; q < 4; q++) {
+            const int b = q * LB;
+            if (warp == 0) {
+                warp_potrf32_v2(S, xd, LT + q * LB * LTLD, b, lane, bad, mant, esum);
+                __threadfence_block();
+                named_bar_arrive(2 + q, 64);
+            }
+            GPP_STAMP(2 + 3 * q)
+            if (q == 3) break;
+            named_bar_sync(1, 224);
+            if (warp >= 1 && warp <= 3 - q) warp_trsm_sub32(S, xd, LT + q * LB * LTLD, (q + warp) * LB, b, lane);
+            named_bar_sync(1, 224);
+            GPP_STAMP(3 + 3 * q)
+            {   // SYRK: A_uw -= L_uq L_wq^T, q < w <= u <= 3; pair 0 = the next diagonal block, owned by warp 0
+                const int m = 3 - q;
+                if (warp < m * (m + 1) / 2) {
+                    int u = 0, w = warp;
+                    while (w > u) { w -= u + 1; u++; }
+                    const int i0 = (q + 1 + u) * LB, j0 = (q + 1 + w) * LB;
+                    acc_zero(acc);
+                    warp_mm32(acc, [&](int r, int k) { return S[(i0 + r) * LLD + b + k]; },
+                              [&](int k, int c) { return S[(j0 + c) * LLD + b + k]; }, g, t);
+#pragma unroll
+                    for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+                        for (int ni = 0; ni < 4; ni++) {
+                            const int r = mi * 8 + g, c = ni * 8 + 2 * t;
+                            double2* p2 = reinterpret_cast<double2*>(S + (i0 + r) * LLD + j0 + c);
+                            double2 v = *p2;
+                            v.x -= acc[mi][ni][0];
+                            v.y -= acc[mi][ni][1];
+                            *p2 = v;
+                        }
+                    __syncwarp();
+                }
+            }
+            GPP_STAMP(4 + 3 * q)
+        }
+        if (warp == 0 && lane == 0) {
+            logdet_part[kb] = log(mant) + (double)esum * 0.6931471805599453;
+            if (bad) atomicOr(info, bad);
+        }
+    }
+    __syncthreads();
+    GPP_STAMP(14)
+
+    // ---- off-diagonal 32-blocks of X = L^-1.  X_ij (i > j) is kept row-major in the unused block (j,i) of S. ----
+    // round 0: T_ik = X_ii L_ik, six blocks
+    if (warp < 6) {
+        int i = 1, k = warp;
+        while (k >= i) { k -= i; i++; }  // warp -> (i,k): (1,0) (2,0) (2,1) (3,0) (3,1) (3,2)
+        acc_zero(acc);
+        const double* Xi = Xd + i * LB * TLD;
+        warp_mm32(acc, [&](int r, int kk) { return Xi[r * TLD + kk]; },
+                  [&](int kk, int n) { return S[(i * LB + kk) * LLD + k * LB + n]; }, g, t);
+        acc_store32(Tr + warp * LB * TLD, TLD, acc, 1.0, g, t);
+    }
+    __syncthreads();
+    // T index of (i,k): i(i-1)/2 + k
+#define GPP_T(i, k) (Tr + ((i) * ((i) - 1) / 2 + (k)) * LB * TLD)
+#define GPP_XOFF(i, j) (S + ((j) * LB) * LLD + (i) * LB)  // row-major container of X_ij, leading dimension LLD
+    // round 1: X_10, X_21, X_32 (stored) and the first terms of X_20, X_31, X_30 (kept in registers)
+    if (warp < 6) {
+        // warps 0..2: (i,j) = (1,0) (2,1) (3,2);  warps 3..5: (2,0) (3,1) (3,0)
+        const int i = (warp < 3) ? warp + 1 : (warp == 3 ? 2 : 3);
+        const int j = (warp < 3) ? warp : (warp == 5 ? 0 : warp - 3);
+        acc_zero(acc);
+        const double* Tij = GPP_T(i, j);
+        const double* Xj = Xd + j * LB * TLD;
+        warp_mm32(acc, [&](int r, int kk) { return Tij[r * TLD + kk]; },
+                  [&](int kk, int n) { return Xj[kk * TLD + n]; }, g, t);
+        if (warp < 3) acc_store32(GPP_XOFF(i, j), LLD, acc, -1.0, g, t);
+    }
+    __syncthreads();
+    // round 2: X_20 = -(P_20 + T_21 X_10) [warp 3], X_31 = -(P_31 + T_32 X_21) [warp 4], P_30 += T_31 X_10 [warp 5]
+    if (warp >= 3 && warp < 6) {
+        const int i = (warp == 3) ? 2 : 3;
+        const int j = (warp == 4) ? 1 : 0;
+        const int k = j + 1;
+        const double* Tik = GPP_T(i, k);
+        const double* Xkj = GPP_XOFF(k, j);
+        warp_mm32(acc, [&](int r, int kk) { return Tik[r * TLD + kk]; },
+                  [&](int kk, int n) { return Xkj[kk * LLD + n]; }, g, t);
+        if (warp < 5) acc_store32(GPP_XOFF(i, j), LLD, acc, -1.0, g, t);
+    }
+    __syncthreads();
+    // round 3: X_30 = -(P_30 + T_32 X_20) [warp 5]
+    if (warp == 5) {
+        const double* Tik = GPP_T(3, 2);
+        const double* Xkj = GPP_XOFF(2, 0);
+        warp_mm32(acc, [&](int r, int kk) { return Tik[r * TLD + kk]; },
+                  [&](int kk, int n) { return Xkj[kk * LLD + n]; }, g, t);
+        acc_store32(GPP_XOFF(3, 0), LLD, acc, -1.0, g, t);
+    }
+    __syncthreads();
+    GPP_STAMP(12)
+#undef GPP_T
+
+    // write back: L (lower) to A_kk, X (lower, zeros above) to M_kk; 16-byte coalesced stores
+    for (int idx = tid; idx < TILE * (TILE / 2); idx += LEAF_THREADS) {
+        const int i = idx >> 6, c = (idx & 63) * 2;
+        const int bi = i >> 5, bc = c >> 5;
+        if (c <= i) {
+            double2 v = *reinterpret_cast<const double2*>(S + i * LLD + c);
+            if (c + 1 > i) v.y = Ab[(long long)i * ld + c + 1];  // keep the entry above the diagonal untouched
+            *reinterpret_cast<double2*>(Ab + (long long)i * ld + c) = v;
+        }
+        double2 x;
+        if (bc > bi) {
+            x.x = 0.0;
+            x.y = 0.0;
+        } else if (bc == bi) {
+            x = *reinterpret_cast<const double2*>(Xd + bi * LB * TLD + (i & 31) * TLD + (c & 31));
+        } else {
+            x = *reinterpret_cast<const double2*>(GPP_XOFF(bi, bc) + (i & 31) * LLD + (c & 31));
+        }
+        *reinterpret_cast<double2*>(Mb + (long long)i * ld + c) = x;
+    }
+#undef GPP_XOFF
+    GPP_STAMP(13)
+#undef GPP_STAMP
+}
+
 inline cudaError_t chol_set_attributes() {
     cudaError_t e = cudaFuncSetAttribute(leaf_potrf_trinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          LEAF_SMEM_BYTES);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(leaf_potrf_trinv_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF2_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
     return gemm_set_attributes();
+}
+
+// leaf generation used by the drivers below (2 = leaf_potrf_trinv_v2_kernel)
+inline int g_leaf_version = 2;
+
+inline cudaError_t launch_leaf(double* A, int ld, int col, double* M, double* logdet_part, int* info, cudaStream_t st,
+                               long long* prof = nullptr) {
+    if (g_leaf_version == 2)
+        leaf_potrf_trinv_v2_kernel<<<1, LEAF_THREADS, LEAF2_SMEM_BYTES, st>>>(A, ld, col, M, logdet_part, info, prof);
+    else
+        leaf_potrf_trinv_kernel<<<1, LEAF_THREADS, LEAF_SMEM_BYTES, st>>>(A, ld, col, M, logdet_part, info);
+    count_launch();
+    return cudaGetLastError();
 }
 
 #define GPP_TRY(x)                      \
@@ -246,9 +565,7 @@ inline cudaError_t potrf_blocked(double* A, double* M, int ld, int T, double* lo
         const int pw = (T - p0 < PANEL_BLOCKS) ? (T - p0) : PANEL_BLOCKS;
         const int pend = p0 + pw;
         for (int col = p0; col < pend; col++) {
-            leaf_potrf_trinv_kernel<<<1, LEAF_THREADS, LEAF_SMEM_BYTES, st>>>(A, ld, col, M, logdet_part, info);
-            count_launch();
-            GPP_TRY(cudaGetLastError());
+            GPP_TRY(launch_leaf(A, ld, col, M, logdet_part, info, st));
             const int below = T - col - 1;
             if (below <= 0) continue;
             {   // TRSM: A[i,col] <- A[i,col] * Linv_col^T   (in place; a CTA only reads its own rows)
@@ -306,6 +623,148 @@ inline cudaError_t potrf_blocked(double* A, double* M, int ld, int T, double* lo
             GPP_TRY(launch_gemm(op, true, true, 1, st));
         }
     }
+    return cudaSuccess;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Look-ahead variant.  The panel factorisation (leaf / TRSM / in-panel update: a chain of small, latency-bound
+// launches) runs on a high-priority side stream and overlaps the bulk of the previous panel's trailing update,
+// which stays on the main stream:
+//
+//   side:  PF(0) . TUn(0) PF(1) . [wait TUr(0)] TUn(1) PF(2) . [wait TUr(1)] TUn(2) ...
+//   main:        [wait PF(0)] TUr(0)            [wait PF(1)] TUr(1) ...
+//
+// PF(p)  = factor panel p;  TUn(p) = update of the NEXT panel's tile columns with panel p (rect + lower filter);
+// TUr(p) = update of everything to the right of the next panel (lower tiles, the O(N^3) part).
+struct CholLookahead {
+    cudaStream_t side = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    std::vector<cudaEvent_t> ev_pf, ev_tu;
+    int panels = 0;
+
+    cudaError_t init(int T) {
+        int lo = 0, hi = 0;
+        GPP_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        GPP_TRY(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, hi));
+        GPP_TRY(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+        GPP_TRY(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
+        panels = (T + PANEL_BLOCKS - 1) / PANEL_BLOCKS;
+        ev_pf.resize(panels);
+        ev_tu.resize(panels);
+        for (int i = 0; i < panels; i++) {
+            GPP_TRY(cudaEventCreateWithFlags(&ev_pf[i], cudaEventDisableTiming));
+            GPP_TRY(cudaEventCreateWithFlags(&ev_tu[i], cudaEventDisableTiming));
+        }
+        return cudaSuccess;
+    }
+    void destroy() {
+        for (auto e : ev_pf) cudaEventDestroy(e);
+        for (auto e : ev_tu) cudaEventDestroy(e);
+        ev_pf.clear();
+        ev_tu.clear();
+        if (fork) cudaEventDestroy(fork);
+        if (join) cudaEventDestroy(join);
+        if (side) cudaStreamDestroy(side);
+        fork = join = nullptr;
+        side = nullptr;
+    }
+};
+
+// factor tile columns [p0, pend) of the panel on stream st (rows p0..T)
+inline cudaError_t panel_factor(double* A, double* M, int ld, int T, int p0, int pend, double* logdet_part, int* info,
+                                cudaStream_t st) {
+    for (int col = p0; col < pend; col++) {
+        GPP_TRY(launch_leaf(A, ld, col, M, logdet_part, info, st));
+        const int below = T - col - 1;
+        if (below <= 0) continue;
+        {   // TRSM: A[i,col] <- A[i,col] * Linv_col^T   (in place; a CTA only reads its own rows)
+            GemmOp op = gemm_default();
+            op.A = A + (long long)(col + 1) * TILE * ld + (long long)col * TILE;
+            op.lda = ld;
+            op.B = M + (long long)col * TILE * ld + (long long)col * TILE;
+            op.ldb = ld;
+            op.C = const_cast<double*>(op.A);
+            op.ldc = ld;
+            op.tiles_m = op.tiles_m_last = below;
+            op.tiles_n = 1;
+            op.klo_c = 0;
+            op.khi_c = 1;
+            GPP_TRY(launch_gemm(op, true, true, 1, st));
+        }
+        const int pc = pend - col - 1;  // panel columns still to update
+        if (pc > 0) {
+            GemmOp op = gemm_default();
+            op.A = A + (long long)(col + 1) * TILE * ld + (long long)col * TILE;
+            op.lda = ld;
+            op.B = op.A;
+            op.ldb = ld;
+            op.C = A + (long long)(col + 1) * TILE * ld + (long long)(col + 1) * TILE;
+            op.ldc = ld;
+            op.tiles_m = op.tiles_m_last = below;
+            op.tiles_n = pc;
+            op.lower_filter = 1;
+            op.lower_off = 0;
+            op.klo_c = 0;
+            op.khi_c = 1;
+            op.alpha = -1.0;
+            op.beta = 1.0;
+            GPP_TRY(launch_gemm(op, true, true, 1, st));
+        }
+    }
+    return cudaSuccess;
+}
+
+// C[i,j] -= sum_{k in [p0,pend)} A[i,k] A[j,k]^T for tile rows i >= r0, tile columns j in [c0, c1), i >= j
+inline cudaError_t trailing_update(double* A, int ld, int T, int p0, int pend, int c0, int c1, cudaStream_t st) {
+    if (c1 <= c0 || c0 >= T) return cudaSuccess;
+    GemmOp op = gemm_default();
+    op.A = A + (long long)c0 * TILE * ld + (long long)p0 * TILE;
+    op.lda = ld;
+    op.B = op.A;
+    op.ldb = ld;
+    op.C = A + (long long)c0 * TILE * ld + (long long)c0 * TILE;
+    op.ldc = ld;
+    op.tiles_m = op.tiles_m_last = T - c0;
+    op.klo_c = 0;
+    op.khi_c = pend - p0;
+    op.alpha = -1.0;
+    op.beta = 1.0;
+    if (c1 >= T) {
+        op.map = MAP_TRI;
+        op.tiles_n = T - c0;
+    } else {
+        op.tiles_n = c1 - c0;
+        op.lower_filter = 1;
+        op.lower_off = 0;
+    }
+    return launch_gemm(op, true, true, 1, st);
+}
+
+inline cudaError_t potrf_lookahead(double* A, double* M, int ld, int T, double* logdet_part, int* info,
+                                   cudaStream_t st, CholLookahead& la) {
+    const int NP = (T + PANEL_BLOCKS - 1) / PANEL_BLOCKS;
+    if (NP > la.panels) return cudaErrorInvalidValue;
+    GPP_TRY(cudaEventRecord(la.fork, st));
+    GPP_TRY(cudaStreamWaitEvent(la.side, la.fork, 0));
+    int last_tu = -1;  // last panel whose TUr was issued on the main stream
+    for (int p = 0; p < NP; p++) {
+        const int p0 = p * PANEL_BLOCKS;
+        const int pend = (p0 + PANEL_BLOCKS < T) ? p0 + PANEL_BLOCKS : T;
+        GPP_TRY(panel_factor(A, M, ld, T, p0, pend, logdet_part, info, la.side));
+        GPP_TRY(cudaEventRecord(la.ev_pf[p], la.side));
+        if (pend >= T) break;
+        const int nend = (pend + PANEL_BLOCKS < T) ? pend + PANEL_BLOCKS : T;
+        if (last_tu >= 0) GPP_TRY(cudaStreamWaitEvent(la.side, la.ev_tu[last_tu], 0));
+        GPP_TRY(trailing_update(A, ld, T, p0, pend, pend, nend, la.side));  // TUn(p)
+        if (nend < T) {
+            GPP_TRY(cudaStreamWaitEvent(st, la.ev_pf[p], 0));
+            GPP_TRY(trailing_update(A, ld, T, p0, pend, nend, T, st));       // TUr(p)
+            GPP_TRY(cudaEventRecord(la.ev_tu[p], st));
+            last_tu = p;
+        }
+    }
+    GPP_TRY(cudaEventRecord(la.join, la.side));
+    GPP_TRY(cudaStreamWaitEvent(st, la.join, 0));
     return cudaSuccess;
 }
 

@@ -27,14 +27,27 @@ inline void count_launch(int k = 1) { g_launches.fetch_add(k, std::memory_order_
 
 constexpr int TILE = 128;        // output tile edge and K block
 constexpr int BK = 16;           // k-chunk staged per pipeline stage
-constexpr int GEMM_THREADS = 256;
-constexpr int GEMM_STAGES = 4;
 constexpr int LDS_KC = BK + 4;   // [row][k] smem row stride (doubles): banks (8g+2t) conflict-free
-constexpr int LDS_KS = TILE + 4; // [k][row] smem row stride (doubles)
-constexpr int STAGE_ELEMS_KC = TILE * LDS_KC;  // 2560
-constexpr int STAGE_ELEMS_KS = BK * LDS_KS;    // 2112
-constexpr int STAGE_ELEMS = STAGE_ELEMS_KC;    // per operand, max of both layouts
-constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * 2 * STAGE_ELEMS * 8;  // 163840
+
+// Two CTA shapes share one kernel body.  BM = 128: one 128x128 output tile per CTA (256 threads,
+// 4 stages, 160 KB, one CTA per SM).  BM = 64: half a tile (64 rows x 128 cols, 128 threads, 3 stages,
+// 90 KB) so that two CTAs are resident per SM and one computes while the other sits at a barrier or
+// in its epilogue.
+template <int BM>
+struct GemmCfg {
+    static constexpr int THREADS = BM * 2;
+    static constexpr int STAGES = (BM == 128) ? 4 : 3;
+    static constexpr int A_LDS_KS = BM + 4;     // [k][row] smem row stride of the A operand
+    static constexpr int B_LDS_KS = TILE + 4;   // [k][row] smem row stride of the B operand
+    static constexpr int A_STAGE = (BM * LDS_KC > BK * A_LDS_KS) ? BM * LDS_KC : BK * A_LDS_KS;
+    static constexpr int B_STAGE = (TILE * LDS_KC > BK * B_LDS_KS) ? TILE * LDS_KC : BK * B_LDS_KS;
+    static constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) * 8;
+    static constexpr int MIN_CTAS = (BM == 128) ? 1 : 2;
+};
+constexpr int GEMM_SMEM_BYTES = GemmCfg<128>::SMEM_BYTES;  // 163840
+
+// CTA shape used by launch_gemm (process-wide; 128 or 64)
+inline int g_gemm_bm = 64;
 
 enum KSel { KSEL_CONST = 0, KSEL_TI = 1, KSEL_TJ = 2 };
 enum TileMap { MAP_RECT = 0, MAP_TRI = 1 };
@@ -76,39 +89,48 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
-// stage one 128 x BK operand chunk into shared memory with 16-byte cp.async
-template <bool KC>
+// stage one R x BK operand chunk into shared memory with 16-byte cp.async (TH threads)
+template <bool KC, int R, int TH>
 __device__ __forceinline__ void load_chunk(double* sm, const double* g, int ld, int tid) {
+    constexpr int PIECES = R * 8 / TH;  // 16-byte pieces per thread
     if (KC) {
-        // global: row r (128 rows), 16 contiguous doubles -> 8 x 16B per row
+        // global: row r (R rows), 16 contiguous doubles -> 8 x 16B per row
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            int c = tid + i * GEMM_THREADS;
+        for (int i = 0; i < PIECES; i++) {
+            int c = tid + i * TH;
             int r = c >> 3, q = c & 7;
             cp_async16(sm + r * LDS_KC + q * 2, g + (long long)r * ld + q * 2);
         }
     } else {
-        // global: k row (16 rows), 128 contiguous doubles -> 64 x 16B per row
+        // global: k row (16 rows), R contiguous doubles -> R/2 x 16B per row
+        constexpr int PPR = R / 2;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            int c = tid + i * GEMM_THREADS;
-            int r = c >> 6, q = c & 63;
-            cp_async16(sm + r * LDS_KS + q * 2, g + (long long)r * ld + q * 2);
+        for (int i = 0; i < PIECES; i++) {
+            int c = tid + i * TH;
+            int r = c / PPR, q = c - r * PPR;
+            cp_async16(sm + r * (R + 4) + q * 2, g + (long long)r * ld + q * 2);
         }
     }
 }
 
-template <bool A_KC, bool B_KC>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_dmma_kernel(const GemmOp op) {
+template <bool A_KC, bool B_KC, int BM>
+__global__ void __launch_bounds__(GemmCfg<BM>::THREADS, GemmCfg<BM>::MIN_CTAS) dgemm_dmma_kernel(const GemmOp op) {
+    using Cfg = GemmCfg<BM>;
+    constexpr int NTH = Cfg::THREADS;
+    constexpr int NST = Cfg::STAGES;
+    constexpr int SPLIT = TILE / BM;  // CTAs per 128-row tile
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x;
     const int z = blockIdx.y;
     const int tm = (z == (int)gridDim.y - 1) ? op.tiles_m_last : op.tiles_m;
+    const int half = (SPLIT == 1) ? 0 : (int)(blockIdx.x % SPLIT);
+    const int tile_id = (SPLIT == 1) ? (int)blockIdx.x : (int)(blockIdx.x / SPLIT);
+    const int r0 = half * BM;  // first row of this CTA inside its 128-row tile
 
     int ti, tj;
     if (op.map == MAP_TRI) {
         // bid -> (ti,tj), tj <= ti, ti ascending (tiles with the longest K range first for LAUUM)
-        int bid = blockIdx.x;
+        int bid = tile_id;
         int t = (int)((sqrt(8.0 * (double)bid + 1.0) - 1.0) * 0.5);
         while ((long long)(t + 1) * (t + 2) / 2 <= bid) t++;
         while ((long long)t * (t + 1) / 2 > bid) t--;
@@ -116,8 +138,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_dmma_kernel(const GemmO
         tj = bid - (int)((long long)t * (t + 1) / 2);
         if (ti >= tm) return;
     } else {
-        ti = blockIdx.x / op.tiles_n;
-        tj = blockIdx.x - ti * op.tiles_n;
+        ti = tile_id / op.tiles_n;
+        tj = tile_id - ti * op.tiles_n;
         if (ti >= tm) return;
         if (op.lower_filter && (ti + op.lower_off < tj)) return;
     }
@@ -129,17 +151,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_dmma_kernel(const GemmO
     const double* Ag = op.A + (long long)z * op.a_zs;
     const double* Bg = op.B + (long long)z * op.b_zs;
     long long a_step, b_step;  // pointer advance per k-chunk
-    if (A_KC) { Ag += (long long)ti * TILE * op.lda + (long long)klo * TILE; a_step = BK; }
-    else      { Ag += (long long)klo * TILE * op.lda + (long long)ti * TILE; a_step = (long long)BK * op.lda; }
+    if (A_KC) { Ag += ((long long)ti * TILE + r0) * op.lda + (long long)klo * TILE; a_step = BK; }
+    else      { Ag += (long long)klo * TILE * op.lda + (long long)ti * TILE + r0; a_step = (long long)BK * op.lda; }
     if (B_KC) { Bg += (long long)tj * TILE * op.ldb + (long long)klo * TILE; b_step = BK; }
     else      { Bg += (long long)klo * TILE * op.ldb + (long long)tj * TILE; b_step = (long long)BK * op.ldb; }
 
     double* sA = smem;
-    double* sB = smem + GEMM_STAGES * STAGE_ELEMS;
+    double* sB = smem + NST * Cfg::A_STAGE;
 
     const int warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int wm0 = (warp >> 1) * 32;  // 4 warps along M
+    const int wm0 = (warp >> 1) * 32;  // BM/32 warps along M
     const int wn0 = (warp & 1) * 64;   // 2 warps along N
 
     double acc[4][8][2];
@@ -150,40 +172,40 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_dmma_kernel(const GemmO
 
     // prologue: S-1 chunks in flight
 #pragma unroll
-    for (int s = 0; s < GEMM_STAGES - 1; s++) {
+    for (int s = 0; s < NST - 1; s++) {
         if (s < nch) {
-            load_chunk<A_KC>(sA + s * STAGE_ELEMS, Ag + s * a_step, op.lda, tid);
-            load_chunk<B_KC>(sB + s * STAGE_ELEMS, Bg + s * b_step, op.ldb, tid);
+            load_chunk<A_KC, BM, NTH>(sA + s * Cfg::A_STAGE, Ag + s * a_step, op.lda, tid);
+            load_chunk<B_KC, TILE, NTH>(sB + s * Cfg::B_STAGE, Bg + s * b_step, op.ldb, tid);
         }
         cp_async_commit();
     }
 
     for (int c = 0; c < nch; c++) {
-        cp_async_wait<GEMM_STAGES - 2>();
+        cp_async_wait<NST - 2>();
         __syncthreads();
         {
-            int cn = c + GEMM_STAGES - 1;
+            int cn = c + NST - 1;
             if (cn < nch) {
-                int s = cn % GEMM_STAGES;
-                load_chunk<A_KC>(sA + s * STAGE_ELEMS, Ag + cn * a_step, op.lda, tid);
-                load_chunk<B_KC>(sB + s * STAGE_ELEMS, Bg + cn * b_step, op.ldb, tid);
+                int s = cn % NST;
+                load_chunk<A_KC, BM, NTH>(sA + s * Cfg::A_STAGE, Ag + cn * a_step, op.lda, tid);
+                load_chunk<B_KC, TILE, NTH>(sB + s * Cfg::B_STAGE, Bg + cn * b_step, op.ldb, tid);
             }
             cp_async_commit();
         }
-        const double* a_s = sA + (c % GEMM_STAGES) * STAGE_ELEMS;
-        const double* b_s = sB + (c % GEMM_STAGES) * STAGE_ELEMS;
+        const double* a_s = sA + (c % NST) * Cfg::A_STAGE;
+        const double* b_s = sB + (c % NST) * Cfg::B_STAGE;
 #pragma unroll
         for (int kk = 0; kk < BK / 4; kk++) {
             double af[4], bf[8];
 #pragma unroll
             for (int mi = 0; mi < 4; mi++) {
                 if (A_KC) af[mi] = a_s[(wm0 + mi * 8 + g) * LDS_KC + kk * 4 + t];
-                else      af[mi] = a_s[(kk * 4 + t) * LDS_KS + wm0 + mi * 8 + g];
+                else      af[mi] = a_s[(kk * 4 + t) * Cfg::A_LDS_KS + wm0 + mi * 8 + g];
             }
 #pragma unroll
             for (int ni = 0; ni < 8; ni++) {
                 if (B_KC) bf[ni] = b_s[(wn0 + ni * 8 + g) * LDS_KC + kk * 4 + t];
-                else      bf[ni] = b_s[(kk * 4 + t) * LDS_KS + wn0 + ni * 8 + g];
+                else      bf[ni] = b_s[(kk * 4 + t) * Cfg::B_LDS_KS + wn0 + ni * 8 + g];
             }
 #pragma unroll
             for (int mi = 0; mi < 4; mi++)
@@ -197,7 +219,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_dmma_kernel(const GemmO
     const double alpha = op.alpha, beta = op.beta;
     if (op.epilogue == EPI_ROWSQ) {
         // rowsq[tj][row] = sum over the tile's 128 columns of (alpha*acc)^2 ; reduce t-lanes then the 2 N-warps
-        double* red = smem;  // [2][128]
+        double* red = smem;  // [2][BM]
 #pragma unroll
         for (int mi = 0; mi < 4; mi++) {
             double s = 0.0;
@@ -209,18 +231,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_dmma_kernel(const GemmO
             }
             s += __shfl_xor_sync(0xffffffffu, s, 1);
             s += __shfl_xor_sync(0xffffffffu, s, 2);
-            if (t == 0) red[(warp & 1) * TILE + wm0 + mi * 8 + g] = s;
+            if (t == 0) red[(warp & 1) * BM + wm0 + mi * 8 + g] = s;
         }
         __syncthreads();
-        if (tid < TILE) {
-            double s = red[tid] + red[TILE + tid];
-            op.rowsq[(long long)tj * op.rowsq_ld + (long long)z * op.c_zs + (long long)ti * TILE + tid] = s;
+        if (tid < BM) {
+            double s = red[tid] + red[BM + tid];
+            op.rowsq[(long long)tj * op.rowsq_ld + (long long)z * op.c_zs + (long long)ti * TILE + r0 + tid] = s;
         }
         return;
     }
 
-    double* Cg = op.C + (long long)z * op.c_zs + (long long)ti * TILE * op.ldc + (long long)tj * TILE;
-    double* Ct = op.C + (long long)z * op.c_zs + (long long)tj * TILE * op.ldc + (long long)ti * TILE;
+    double* Cg = op.C + (long long)z * op.c_zs + ((long long)ti * TILE + r0) * op.ldc + (long long)tj * TILE;
+    double* Ct = op.C + (long long)z * op.c_zs + (long long)tj * TILE * op.ldc + (long long)ti * TILE + r0;
     const bool do_mirror = op.mirror && (ti != tj);
 #pragma unroll
     for (int mi = 0; mi < 4; mi++) {
@@ -246,30 +268,45 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_dmma_kernel(const GemmO
     }
 }
 
+template <int BM>
+inline cudaError_t launch_gemm_bm(const GemmOp& op, bool a_kc, bool b_kc, int nt, int nbatch, cudaStream_t st) {
+    using Cfg = GemmCfg<BM>;
+    dim3 grid(nt * (TILE / BM), nbatch), block(Cfg::THREADS);
+    if (a_kc && b_kc) dgemm_dmma_kernel<true, true, BM><<<grid, block, Cfg::SMEM_BYTES, st>>>(op);
+    else if (a_kc && !b_kc) dgemm_dmma_kernel<true, false, BM><<<grid, block, Cfg::SMEM_BYTES, st>>>(op);
+    else if (!a_kc && !b_kc) dgemm_dmma_kernel<false, false, BM><<<grid, block, Cfg::SMEM_BYTES, st>>>(op);
+    else dgemm_dmma_kernel<false, true, BM><<<grid, block, Cfg::SMEM_BYTES, st>>>(op);
+    return cudaGetLastError();
+}
+
 inline cudaError_t launch_gemm(const GemmOp& op, bool a_kc, bool b_kc, int nbatch, cudaStream_t st) {
     int nt;
     if (op.map == MAP_TRI) nt = op.tiles_m * (op.tiles_m + 1) / 2;
     else nt = op.tiles_m * op.tiles_n;
     if (nt <= 0 || nbatch <= 0) return cudaSuccess;
-    dim3 grid(nt, nbatch), block(GEMM_THREADS);
     count_launch();
-    if (a_kc && b_kc) dgemm_dmma_kernel<true, true><<<grid, block, GEMM_SMEM_BYTES, st>>>(op);
-    else if (a_kc && !b_kc) dgemm_dmma_kernel<true, false><<<grid, block, GEMM_SMEM_BYTES, st>>>(op);
-    else if (!a_kc && !b_kc) dgemm_dmma_kernel<false, false><<<grid, block, GEMM_SMEM_BYTES, st>>>(op);
-    else dgemm_dmma_kernel<false, true><<<grid, block, GEMM_SMEM_BYTES, st>>>(op);
-    return cudaGetLastError();
+    if (g_gemm_bm == 64) return launch_gemm_bm<64>(op, a_kc, b_kc, nt, nbatch, st);
+    return launch_gemm_bm<128>(op, a_kc, b_kc, nt, nbatch, st);
+}
+
+template <int BM>
+inline cudaError_t gemm_set_attributes_bm() {
+    cudaError_t e;
+    const int b = GemmCfg<BM>::SMEM_BYTES;
+    e = cudaFuncSetAttribute(dgemm_dmma_kernel<true, true, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(dgemm_dmma_kernel<true, false, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(dgemm_dmma_kernel<false, false, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(dgemm_dmma_kernel<false, true, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
+    return e;
 }
 
 inline cudaError_t gemm_set_attributes() {
-    cudaError_t e;
-    e = cudaFuncSetAttribute(dgemm_dmma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+    cudaError_t e = gemm_set_attributes_bm<128>();
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(dgemm_dmma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(dgemm_dmma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(dgemm_dmma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
-    return e;
+    return gemm_set_attributes_bm<64>();
 }
 
 inline GemmOp gemm_default() {

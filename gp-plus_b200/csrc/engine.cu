@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -87,6 +88,8 @@ struct gpp_handle {
     cudaEvent_t ev[EV_COUNT];
     bool ev_valid[EV_COUNT];
     gpp_timings tm;
+    CholLookahead la;
+    bool use_lookahead = true;
 };
 
 static const double* hyp_w(const gpp_handle* h) { return h->hyp; }
@@ -130,6 +133,7 @@ extern "C" void gpp_destroy(gpp_handle* h) {
     if (h->res_host) cudaFreeHost(h->res_host);
     if (h->gz_host) cudaFreeHost(h->gz_host);
     for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(h->ev[i]);
+    h->la.destroy();
     if (h->st) cudaStreamDestroy(h->st);
     delete h;
 }
@@ -190,6 +194,14 @@ extern "C" int gpp_create(const gpp_problem* p, int device, gpp_handle** out) {
     for (int i = 0; i < EV_COUNT; i++) CKH(cudaEventCreate(&h->ev[i]));
     CKH(chol_set_attributes());
     CKH(cov_set_attributes());
+    {
+        // development switches (defaults are the production configuration)
+        const char* e;
+        if ((e = getenv("GPP_CHOL")) != nullptr) h->use_lookahead = strcmp(e, "blocked") != 0;
+        if ((e = getenv("GPP_LEAF")) != nullptr) g_leaf_version = atoi(e) == 1 ? 1 : 2;
+        if ((e = getenv("GPP_GEMM_BM")) != nullptr) g_gemm_bm = atoi(e) == 64 ? 64 : 128;
+    }
+    CKH(h->la.init(h->T));
 
     CKH(dev_alloc(&h->xq, (size_t)n * h->dq));
     CKH(dev_alloc(&h->y, (size_t)n));
@@ -358,7 +370,10 @@ static int stage_factor(gpp_handle* h, int* info_out) {
     ca.diag_add = h->diag_add;
     CK(launch_cov(ca, h->kernel, h->st));
     mark(h, EV_COV);
-    CK(potrf_blocked(h->A, h->M, (int)h->np, h->T, h->logdet_part, h->info, h->st));
+    if (h->use_lookahead)
+        CK(potrf_lookahead(h->A, h->M, (int)h->np, h->T, h->logdet_part, h->info, h->st, h->la));
+    else
+        CK(potrf_blocked(h->A, h->M, (int)h->np, h->T, h->logdet_part, h->info, h->st));
     mark(h, EV_CHOL);
     CK(cudaMemcpyAsync(h->info_host, h->info, sizeof(int), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));

@@ -110,9 +110,12 @@ def test_jitter_ladder_and_error_mapping():
     from gpplus_b200 import _engine as E
     from oracle import gp_oracle as O
     p = make_problem(64, 2, 0, seed=27)
-    p["xq"][1] = p["xq"][0]  # duplicated point + (almost) no noise: singular K_y
+    p["xq"][1] = p["xq"][0]  # duplicated point: K has a zero eigenvalue
     h = make_hyper(p, seed=11)
-    h["noise"] = np.array([1e-17])
+    # natural-parameter ABI: a slightly negative diagonal term makes K_y indefinite by a margin far above
+    # rounding (lambda_min = -5e-9), so the outcome of the first rung does not depend on the rounding of the
+    # factorisation; the 1e-8 rung of psd_safe_cholesky repairs it (lambda_min = +5e-9)
+    h["noise"] = np.array([-5e-9])
     eng = E.Engine(**engine_kwargs(p))
     try:
         try:
