@@ -1,0 +1,219 @@
+"""Multi-fidelity cost-aware Bayesian optimisation loop (reference: bayesian_optimizations/BO_GP_plus.py).
+
+``BO`` keeps the reference's signature, bookkeeping (best-so-far per source, cumulative cost, convergence test
+on the variance of the last ``max_iter`` incumbents) and return value ``(bestf, cumulative_cost)``.  Its two
+inner steps are re-pointed at the B200 engine:
+
+* candidate-TABLE branch (``data_gen_func`` is an array; BO_GP_plus.py:167-211): the per-source
+  ``predict`` + ``AF_*_Engineering`` + ``torch.argmax(torch.cat(scores))`` sequence becomes ONE fused
+  predict + acquisition + arg-max pass (``gpp_acq_argmax``), with the table split into contiguous chunks over
+  the ranks of the process group and a 16-byte all-gather for the arg-max (``parallel.global_argmax``);
+* FUNCTION branch (``data_gen_func`` is callable; :84-165): the 12 random-start L-BFGS-B searches per source
+  run in this process against the factor cached on the GPU (the reference spawns loky workers, each
+  re-pickling the model).
+
+Deviations from the reference source, which cannot run as published: it constructs the model with
+``GP_Plus(Xtrain, ytrain, qual_index, IS=IS)`` although ``GP_Plus`` has neither a third positional
+``qual_index`` nor an ``IS`` argument (models/gp_plus.py:79-108); here the model is built with
+``qual_dict=qual_index, interval_score=IS``.  Quirks that change results are kept and marked QUIRK.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .. import _engine, parallel
+from .AFs import AF_HF, AF_LF
+
+_KIND = {"HF": _engine.ACQ_HF, "LF": _engine.ACQ_LF, "EI": _engine.ACQ_EI}
+
+
+def acquisition_table_argmax(model, table_x, best_values: Sequence[float], cost_by_source: Sequence[float],
+                             maximize: bool = True, si: float = 0.0, kinds: Optional[Sequence[str]] = None,
+                             return_scores: bool = False):
+    """Arg-max of the cost-scaled acquisition over a candidate table (BO_GP_plus.py:183-194).
+
+    ``table_x`` [M, d] holds model inputs whose LAST column is the source index.  Candidates are scored in
+    source-major order -- all rows of source 0 (AF_HF_Engineering), then source 1, ... (AF_LF_Engineering) --
+    exactly the order of ``torch.cat(scores)`` in the reference, with ``include_noise=False``.  Returns
+    ``(best_score, index_in_source_major_order, order)`` where ``order`` maps that position back to a row of
+    ``table_x``; with ``return_scores`` the source-major score vector of THIS rank's chunk is appended.
+    """
+    x = torch.as_tensor(np.asarray(table_x), dtype=torch.float64)
+    n_src = len(best_values)
+    src = x[:, -1].round().to(torch.int64)
+    order = torch.argsort(src, stable=True)
+    order = order[(src[order] >= 0) & (src[order] < n_src)]
+    xs = x[order]
+    src_sorted = src[order].numpy().astype(np.int32)
+    m = xs.shape[0]
+    kinds = list(kinds) if kinds is not None else ["HF"] + ["LF"] * (n_src - 1)
+    eng = model._ensure_factor()
+
+    # level / mean indices exactly as model.predict would derive them for each per-source slice
+    lvl = np.zeros(m, dtype=np.int32) if eng.dz > 0 else None
+    mean_idx = None
+    bounds = np.searchsorted(src_sorted, np.arange(n_src + 1))
+    for s in range(n_src):
+        lo, hi = int(bounds[s]), int(bounds[s + 1])
+        if hi <= lo:
+            continue
+        part = xs[lo:hi]
+        if lvl is not None:
+            lvl[lo:hi] = model._level_index(part, False)  # QUIRK: eval-mode setlevels acts per slice (gp_plus.py:1081)
+        mi = model._mean_index(part)
+        if mi is not None:
+            if mean_idx is None:
+                mean_idx = np.zeros(m, dtype=np.int32)
+            mean_idx[lo:hi] = mi
+    cols = model._quant_columns()
+    xq = np.ascontiguousarray(xs[:, cols].numpy()) if len(cols) > 0 else np.zeros((m, 0))
+
+    lo, hi = parallel.shard_range(m)
+    if hi > lo:
+        res = eng.acq_argmax(
+            xq[lo:hi], src_sorted[lo:hi], cost=list(cost_by_source), kind_by_cost=[_KIND[k] for k in kinds],
+            best_f=list(best_values), level_idx=None if lvl is None else lvl[lo:hi],
+            mean_idx=None if mean_idx is None else mean_idx[lo:hi], maximize=maximize, si=si,
+            y_min=float(model.y_min), y_std=float(model.y_std), return_scores=return_scores)
+        score, idx = res[0], int(res[1]) + lo
+    else:
+        res, score, idx = (None, None, np.zeros(0)), -np.inf, -1
+    score, idx = parallel.global_argmax(score, idx)
+    if return_scores:
+        return score, idx, order.numpy(), res[2]
+    return score, idx, order.numpy()
+
+
+def BO(Xtrain=None, ytrain=None, costs=None, l_bound=None, u_bound=None, xmean=None, xstd=None, qual_index=None,
+       data_gen_func=None, n_train=None, maximize_flag=False, one_iter=False, max_cost=40000, MF=True, AF_hf=AF_HF,
+       AF_lf=AF_LF, max_iter=2, IS=True, model_kwargs: Optional[Dict] = None, fit_kwargs: Optional[Dict] = None):
+    from ..models import GP_Plus
+    from ..optim import fit_model_scipy
+
+    model_kwargs = dict(model_kwargs or {})
+    fit_kwargs = dict(fit_kwargs or {})
+    fit_kwargs.setdefault("bounds", True)
+    ymin_list, xmin_list, cumulative_cost, bestf, Fidelity = [], [], [], [], []
+    num_fidelity = list(qual_index.values())[-1]
+
+    def cost_fun(x):
+        return costs[str(int(x))]
+
+    def bestf_calculator(ytrain, Xtrain):
+        pick = (lambda v: v.max()) if maximize_flag else (lambda v: v.min())
+        if MF:
+            return [pick(ytrain[Xtrain[:, -1] == i]).reshape(-1).item() for i in range(num_fidelity)]
+        return [pick(ytrain).reshape(-1).item()]
+
+    def fit_new_model(Xtrain, ytrain):
+        model = GP_Plus(Xtrain, ytrain, qual_dict=qual_index, interval_score=IS, **model_kwargs)
+        fit_model_scipy(model, **fit_kwargs)
+        return model
+
+    def run_scipy(EI, best_f, bound, model, fidelity):
+        from scipy.optimize import minimize
+        random_seed = np.random.choice(range(0, 1000), size=12, replace=False)
+        lo = list(l_bound) + [fidelity]
+        hi = list(u_bound) + [fidelity]
+        best_val, best_x = np.inf, None
+        for k in range(12):
+            np.random.seed(random_seed[k])
+            start = np.random.uniform(lo, hi).reshape(-1)
+            start[-1] = np.round(start[-1])
+            res = minimize(lambda s: float(EI(s, best_f, model, np.array(xmean), np.array(xstd), cost_fun)), start,
+                           bounds=bound)
+            if res.fun < best_val:  # np.argmin keeps the first minimum
+                best_val, best_x = float(res.fun), res.x
+        return best_val, best_x
+
+    def converged():
+        return len(bestf) > max_iter and np.var(bestf[-max_iter:]) < 1e-6
+
+    if callable(data_gen_func):
+        Xtrain = torch.as_tensor(np.asarray(Xtrain), dtype=torch.float64)
+        ytrain = torch.as_tensor(np.asarray(ytrain), dtype=torch.float64).reshape(-1)
+        initial_cost = np.sum(list(map(cost_fun, Xtrain[:, -1])))
+        cumulative_cost.append(initial_cost)
+        problem = lambda x: data_gen_func(False, x)  # noqa: E731
+        while cumulative_cost[-1] < max_cost:
+            best_values = bestf_calculator(ytrain, Xtrain)
+            bestf.append(best_values[0])
+            if converged():
+                break
+            model = fit_new_model(Xtrain, ytrain)
+            X_list, y_list = [], []
+            for i in range(num_fidelity):
+                bound = tuple(list(zip(l_bound, u_bound)) + [(i, i)])
+                # QUIRK: every source is scored against the HIGH-fidelity incumbent best_values[0] (:135,:140)
+                val, xbest = run_scipy(AF_hf if i == 0 else AF_lf, best_values[0], bound, model, i)
+                X_list.append(xbest)
+                y_list.append(val)
+            model.release_engine()
+            temp = torch.tensor(X_list[int(np.argmin(y_list))])
+            ynew = torch.as_tensor(problem(temp.unsqueeze(0)), dtype=torch.float64)
+            if MF:
+                Xnew = np.concatenate([((temp[0:-1] - xmean) / xstd).reshape(1, -1), temp[-1].reshape(-1, 1)], axis=-1)
+            else:
+                Xnew = ((temp - xmean) / xstd).reshape(1, -1)
+            Xnew = np.asarray(Xnew, dtype=np.float64)
+            Xtrain = torch.cat([Xtrain, torch.tensor(Xnew.reshape(1, -1))])
+            ytrain = torch.cat([ytrain, ynew.reshape(-1)])
+            ymin_list.append(ynew.reshape(-1))
+            xmin_list.append(Xnew)
+            cumulative_cost.append(initial_cost + cost_fun(Xnew[0][-1]))
+            initial_cost = cumulative_cost[-1]
+            Fidelity.append(Xnew[0][-1])
+            if one_iter:
+                bestf.append(bestf_calculator(ytrain, Xtrain)[0])
+                break
+    else:
+        table = np.asarray(data_gen_func, dtype=np.float64)  # columns: inputs..., source, y
+        Xtrain = np.empty((0, table.shape[1] - 1))
+        ytrain = np.empty((0,))
+        for i in range(num_fidelity):
+            rows = table[table[:, -2] == i]
+            random_index = np.random.randint(0, len(rows), n_train[i])
+            Xtrain = np.append(Xtrain, rows[random_index][:, 0:-1], axis=0)
+            # QUIRK: the reference reads y from the FULL table at the per-source positions (:173)
+            ytrain = np.append(ytrain, table[random_index][:, -1], axis=0)
+        Xtrain, ytrain = torch.tensor(Xtrain), torch.tensor(ytrain)
+        initial_cost = np.sum(list(map(cost_fun, Xtrain[:, -1])))
+        cumulative_cost.append(initial_cost)
+        cost_by_source = [cost_fun(i) for i in range(num_fidelity)]
+        while cumulative_cost[-1] < max_cost:
+            best_values = bestf_calculator(ytrain, Xtrain)
+            bestf.append(best_values[0])
+            if converged():
+                break
+            model = fit_new_model(Xtrain, ytrain)
+            _, index, _ = acquisition_table_argmax(model, table[:, 0:-1], best_values, cost_by_source,
+                                                   maximize=maximize_flag)
+            model.release_engine()
+            # QUIRK: the arg-max position in source-major order indexes the ORIGINAL table (:194-196)
+            Xnew = torch.tensor(table[index][0:-1])
+            ynew = table[index][-1]
+            Xtrain = torch.cat([Xtrain, Xnew.reshape(1, -1)])
+            ytrain = torch.cat([ytrain, torch.tensor(ynew).reshape(-1)], dim=0)
+            ymin_list.append(np.asarray(ynew).reshape(-1))
+            xmin_list.append(Xnew)
+            cumulative_cost.append(initial_cost + cost_fun(Xnew[-1]))
+            initial_cost = cumulative_cost[-1]
+            Fidelity.append(Xnew[-1])
+            if one_iter:
+                bestf.append(bestf_calculator(ytrain, Xtrain)[0])
+                break
+    return np.array(bestf), np.array(cumulative_cost)
+
+
+def Visualize_BO(bestf, cost):
+    try:
+        import matplotlib.pyplot as plt
+    except ImportError as e:  # matplotlib is an optional dependency of the plotting helper only
+        raise ImportError("Visualize_BO needs matplotlib") from e
+    plt.scatter(cost, bestf)
+    plt.ylabel("y^*")
+    plt.xlabel("cost")
+    plt.show()

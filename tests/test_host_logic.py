@@ -220,3 +220,42 @@ def test_restart_and_candidate_sharding_world2_gloo(tmp_path):
         out, _ = pr.communicate(timeout=240)
         assert pr.returncode == 0, out.decode()
         assert ("rank %d ok" % r) in out.decode()
+
+
+def test_acquisition_functions_match_the_oracle_formulas():
+    """AF_*_Engineering (AFs.py:102-159) against the oracle's acquisition(); AF_LF/HF/EI point objectives
+    (AFs.py:1-99) against the same formulas through a stub model."""
+    from gpplus_b200.bayesian_optimizations import AF_EI, AF_HF, AF_HF_Engineering, AF_LF, AF_LF_Engineering
+    from oracle import gp_oracle as O
+    rng = np.random.default_rng(5)
+    m = 40
+    mean = torch.tensor(rng.standard_normal((m, 1)))
+    std = torch.tensor(0.1 + rng.random((m, 1)))
+    xval = torch.tensor(np.hstack([rng.standard_normal((m, 3)), rng.integers(0, 3, (m, 1)).astype(float)]))
+    costs = {"0": 1000.0, "1": 100.0, "2": 10.0}
+    cost_fun = lambda s: costs[str(int(s))]  # noqa: E731
+    cvec = np.array([cost_fun(s) for s in xval[:, -1]])
+    for maximize in (True, False):
+        for best_f in (0.3, -0.7):
+            hf = AF_HF_Engineering(best_f, mean, std, xval, cost_fun, maximize=maximize, si=0.05)
+            lf = AF_LF_Engineering(best_f, mean, std, xval, cost_fun, maximize=maximize, si=0.05)
+            assert hf.shape == (m,) and lf.shape == (m,)
+            ref_hf = O.acquisition(mean.reshape(-1), std.reshape(-1), 0, best_f, cvec, maximize=maximize, si=0.05)
+            ref_lf = O.acquisition(mean.reshape(-1), std.reshape(-1), 1, best_f, cvec, maximize=maximize, si=0.05)
+            assert np.allclose(hf.numpy(), ref_hf, rtol=1e-13, atol=1e-15)
+            assert np.allclose(lf.numpy(), ref_lf, rtol=1e-13, atol=1e-15)
+
+    class Stub:
+        def predict(self, x, return_std=True, include_noise=True):
+            assert include_noise and x.shape == (1, 4)
+            self.seen = x.clone()
+            return torch.tensor([0.4]), torch.tensor([0.2])
+
+    stub = Stub()
+    xmean, xstd = np.array([1.0, 2.0, 3.0]), np.array([2.0, 4.0, 8.0])
+    sample = np.array([3.0, 6.0, 11.0, 2.0])
+    for fn, kind in ((AF_HF, 0), (AF_LF, 1), (AF_EI, 2)):
+        val = fn(sample, 0.1, stub, xmean, xstd, cost_fun, maximize=False)
+        ref = -O.acquisition(np.array([0.4]), np.array([0.2]), kind, 0.1, np.array([10.0]), maximize=False)
+        assert np.allclose(np.asarray(val).reshape(-1), ref, rtol=1e-13)
+        assert np.allclose(stub.seen.numpy(), [[1.0, 1.0, 1.0, 2.0]])

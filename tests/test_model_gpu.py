@@ -142,3 +142,38 @@ def test_adam_and_continuation_paths_drive_the_same_engine():
     nll, history = fit_model_continuation(m2, num_restarts=1, bounds=True)
     assert np.isfinite(nll) and len(history["noise_history"]) >= 1
     assert not m2.likelihood.raw_noise.requires_grad
+
+
+def test_fused_table_acquisition_matches_slice_by_slice_reference_sequence():
+    """BO's candidate-table step (BO_GP_plus.py:183-194): per-source predict(include_noise=False) +
+    AF_HF/LF_Engineering + argmax(cat(scores)) versus the single fused predict+acquisition+arg-max pass."""
+    from gpplus_b200.bayesian_optimizations import AF_HF_Engineering, AF_LF_Engineering, acquisition_table_argmax
+    m, spec, Xte, yte = _c3()
+    torch.manual_seed(3)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_(0.1 * torch.randn_like(p))
+    rng = np.random.default_rng(11)
+    M = 3000
+    Xq = rng.standard_normal((M, 10))
+    src = rng.integers(0, 4, (M, 1)).astype(float)
+    table = np.hstack([Xq, src])
+    costs = {"0": 1000.0, "1": 100.0, "2": 10.0, "3": 100.0}
+    cost_fun = lambda s: costs[str(int(s))]  # noqa: E731
+    ytr = m.y_min + m.y_std * m.train_targets
+    best = [float(ytr[m.train_inputs[0][:, -1] == i].max()) for i in range(4)]
+    for maximize in (True, False):
+        scores = []
+        for i in range(4):
+            part = torch.tensor(table[table[:, -1] == i])
+            mu, sd = m.predict(part, return_std=True, include_noise=False)
+            af = AF_HF_Engineering if i == 0 else AF_LF_Engineering
+            scores.append(af(best[i], mu.reshape(-1, 1), sd.reshape(-1, 1), part, cost_fun, maximize=maximize))
+        ref_scores = torch.cat(scores, dim=0).numpy()
+        ref_index = int(np.argmax(ref_scores))
+        score, index, order, got = acquisition_table_argmax(m, table, best, [costs[str(i)] for i in range(4)],
+                                                            maximize=maximize, return_scores=True)
+        assert index == ref_index
+        assert np.allclose(got, ref_scores, rtol=1e-9, atol=1e-14)
+        assert abs(score - ref_scores[ref_index]) <= 1e-9 * abs(ref_scores[ref_index])
+        assert np.array_equal(table[order][:, -1], np.sort(table[:, -1]))
