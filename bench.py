@@ -313,6 +313,172 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+
+# ------------------------------------------------------------------------------------------------
+# secondary workloads (not the driver's default line): BASELINE configs[1] and configs[4]
+def _dist_setup():
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return world, rank, local
+
+
+def _c2_problem():
+    """Borehole mixed-variable emulation with a categorical latent map (Example 02): n=500, two categorical
+    inputs x 5 levels, weighted rough-RBF kernel."""
+    import torch
+    from gpplus_b200.preprocessing import train_test_split_normalizeX
+    from gpplus_b200.test_functions import borehole_mixed_variables
+    from gpplus_b200.utils import set_seed
+    set_seed(4)
+    qd = {0: 5, 5: 5}
+    X, y = borehole_mixed_variables(n=2000, qual_dict=qd, random_state=4)
+    Xtr, Xte, ytr, yte = train_test_split_normalizeX(X, y, test_size=0.75, qual_dict=qd)
+    return Xtr, ytr, Xte, yte, qd
+
+
+def run_fit(args):
+    """64-restart multi-start MAP fit (fit_model_scipy, L-BFGS-B, reference defaults) of configs[1]."""
+    import torch
+    from gpplus_b200 import _engine as E
+    from gpplus_b200.models import GP_Plus
+    from gpplus_b200.models.gpregression import set_default_device
+    from gpplus_b200.optim import fit_model_scipy
+    from gpplus_b200.optim.mll_scipy import MLLObjective, _sample_from_prior
+    if args.impl == "reference":
+        return run_fit_reference(args)
+    world, rank, local = _dist_setup()
+    set_default_device(local)
+    Xtr, ytr, Xte, yte, qd = _c2_problem()
+    model = GP_Plus(Xtr, ytr, qual_dict=qd, dtype=torch.float64)
+    torch.manual_seed(0)
+    obj = MLLObjective(model, True, [0, 0])
+    theta0 = [_sample_from_prior(model) for _ in range(args.restarts + 1)]
+    fit_model_scipy(model, num_restarts=0, theta0_list=theta0[:2])  # warm-up: library load, first launches
+    torch.cuda.synchronize()
+    l0 = E.launch_count()
+    t0 = time.time()
+    res, best = fit_model_scipy(model, add_prior=True, num_restarts=args.restarts, theta0_list=theta0)
+    torch.cuda.synchronize()
+    dt = time.time() - t0
+    if rank == 0:
+        nfev = sum(int(r.nfev) for r in res if not isinstance(r, Exception))
+        failed = sum(1 for r in res if isinstance(r, Exception))
+        mu = model.predict(Xte, return_std=False)
+        rrmse = float(torch.sqrt(torch.mean((mu - yte) ** 2)) / yte.std())
+        print(json.dumps({
+            "metric": "64-restart fit time", "value": dt, "unit": "s", "n_gpus": world, "higher_is_better": False,
+            "scaling": "strong", "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "borehole mixed-variable, n=%d, 2 categorical x 5 levels, rough-RBF x latent map, "
+                                   "%d restarts (+1), L-BFGS-B reference defaults" % (Xtr.shape[0], args.restarts)},
+            "objective_evals": nfev, "evals_per_s": nfev / dt, "failed_starts": failed, "best_neg_log_posterior": best,
+            "test_rrmse": rrmse, "gpu_launches": E.launch_count() - l0}), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def run_fit_reference(args):
+    """CPU arm of the fit workload: the model-level oracle (the reference's torch path restated) driven by the same
+    scipy L-BFGS-B, from the same starts, on a bounded number of restarts; scaled to restarts+1 runs spread over
+    the host cores the way joblib(n_jobs=-1) would."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import torch
+    from scipy.optimize import minimize
+    from gpplus_b200.models import GP_Plus
+    from gpplus_b200.optim.mll_scipy import _sample_from_prior
+    from oracle import gpplus_oracle as GO
+    Xtr, ytr, Xte, yte, qd = _c2_problem()
+    model = GP_Plus(Xtr, ytr, qual_dict=qd, dtype=torch.float64)
+    torch.manual_seed(0)
+    theta0 = [_sample_from_prior(model) for _ in range(args.restarts + 1)]
+    spec = {"X": Xtr.numpy(), "y": ytr.numpy(), "qual_dict": qd, "kernel": "Rough_RBF"}
+    torch.set_num_threads(1)  # one restart per core, as loky workers do
+    sample = min(3, len(theta0))
+    t0 = time.time()
+    nfev = 0
+    for th in theta0[:sample]:
+        try:
+            r = minimize(lambda x: GO.neg_log_posterior(spec, x), th, jac=True, method="L-BFGS-B",
+                         options={"ftol": 1e-6, "gtol": 1e-5, "maxfun": 5000, "maxiter": 2000})
+            nfev += int(r.nfev)
+        except Exception:
+            pass
+    dt = time.time() - t0
+    cores = os.cpu_count() or 1
+    waves = -(-(args.restarts + 1) // cores)
+    est = dt / sample * waves
+    print(json.dumps({
+        "impl": "reference", "metric": "64-restart fit time", "value": est, "unit": "s", "higher_is_better": False,
+        "config": {"workload": "borehole mixed-variable, n=%d, %d restarts (+1)" % (Xtr.shape[0], args.restarts)},
+        "cpu_baseline": {"value": est, "unit": "s", "cores": cores, "kind": "port",
+                         "sample": "%d sequential single-thread oracle L-BFGS-B runs (%.1f s, %d evals), scaled to "
+                                   "ceil(%d/%d) waves of one run per core" % (sample, dt, nfev, args.restarts + 1, cores)}
+    }), flush=True)
+
+
+def run_acq(args):
+    """MFBO borehole (Example 04): predictive mean/variance + cost-aware acquisition + arg-max over M candidates,
+    candidates sharded over ranks."""
+    import torch
+    from gpplus_b200 import _engine as E
+    from gpplus_b200.bayesian_optimizations import acquisition_table_argmax
+    from gpplus_b200.models import GP_Plus
+    from gpplus_b200.models.gpregression import set_default_device
+    from gpplus_b200.optim import fit_model_scipy
+    from gpplus_b200.preprocessing.normalizeX import standard
+    from gpplus_b200.test_functions.multi_fidelity import BH_MAX, BH_MIN, Borehole_MF_BO
+    from scipy.stats.qmc import Sobol, scale
+    world, rank, local = _dist_setup()
+    set_default_device(local)
+    np.random.seed(0)
+    torch.manual_seed(0)
+    qd = {8: 5}
+    U, y = Borehole_MF_BO(True, {"0": 5, "1": 5, "2": 50, "3": 5, "4": 50})
+    U, umean, ustd = standard(torch.tensor(U), qd)
+    model = GP_Plus(U, torch.tensor(y).reshape(-1), qual_dict=qd, dtype=torch.float64, multiple_noise=False)
+    fit_model_scipy(model, num_restarts=8, bounds=True)
+    M = args.candidates
+    cand = scale(Sobol(d=8, seed=1).random(M), l_bounds=BH_MIN, u_bounds=BH_MAX)
+    cand = (cand - umean.numpy()) / ustd.numpy()
+    src = np.random.RandomState(1).randint(0, 5, size=(M, 1)).astype(np.float64)
+    table = np.hstack([cand, src])
+    costs = [1000.0, 100.0, 10.0, 100.0, 10.0]
+    ytr = torch.tensor(y).reshape(-1)
+    best = [float(ytr[U[:, -1] == i].min()) for i in range(5)]
+    acquisition_table_argmax(model, table[:4096], best, costs, maximize=False)  # warm-up
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(max(1, args.steps)):
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        t0 = time.time()
+        score, idx, order = acquisition_table_argmax(model, table, best, costs, maximize=False)
+        torch.cuda.synchronize()
+        times.append(time.time() - t0)
+    dt = min(times)
+    if rank == 0:
+        print(json.dumps({
+            "metric": "acquisition candidates/sec (predict mean/var + AF + arg-max)", "value": M / dt,
+            "unit": "candidates/s", "n_gpus": world, "higher_is_better": True, "scaling": "strong", "dtype": "f64",
+            "data": "synthetic", "ms_per_step": 1e3 * dt,
+            "config": {"workload": "MFBO borehole, n_train=%d, 5 sources, %d Sobol candidates from HOST memory "
+                                   "(source-major sort, level lookup, H2D, fused predict+AF+arg-max, D2H of the winner)"
+                                   % (U.shape[0], M)},
+            "best": {"score": score, "index": int(idx)}}), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -320,10 +486,19 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=N_HEADLINE)
+    ap.add_argument("--workload", default="mll", choices=["mll", "fit", "acq"],
+                    help="mll (default, the headline metric) | fit: 64-restart fit of BASELINE configs[1] | "
+                         "acq: predictive mean/var + acquisition arg-max over --candidates (configs[4])")
+    ap.add_argument("--restarts", type=int, default=64)
+    ap.add_argument("--candidates", type=int, default=1000000)
     args = ap.parse_args()
-    if args.warmup < 3 and args.impl == "ours":
+    if args.warmup < 3 and args.impl == "ours" and args.workload == "mll":
         args.warmup = 3
-    if args.impl == "reference":
+    if args.workload == "fit":
+        run_fit(args)
+    elif args.workload == "acq":
+        run_acq(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

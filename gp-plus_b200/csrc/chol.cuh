@@ -70,7 +70,7 @@ __device__ __forceinline__ void warp_potrf_inv32(double* S, double* xd, int b, i
 #pragma unroll
         for (int j = 0; j < LB; j++) {
             const double d = __shfl_sync(FULL, a[j], j);
-            if (!(d > 0.0)) bad |= (d != d) ? 2 : 1;
+            if (!(d > 0.0) && bad == 0) bad = (d != d) ? 2 : 1;  // the first failing pivot decides
             const double l = sqrt(d);
             const double inv = 1.0 / l;
             int ex;
@@ -177,7 +177,7 @@ leaf_potrf_trinv_kernel(double* A, int ld, int kb, double* M, double* logdet_par
     }
     if (tid == 0) {
         logdet_part[kb] = logacc;
-        if (bad) atomicOr(info, bad);
+        if (bad && *info == 0) atomicOr(info, bad);  // leaves run in sequence: an earlier failure wins
     }
 
     // off-diagonal 32-blocks of X = L^-1 by block forward substitution, one block-diagonal distance at a time:
@@ -274,7 +274,7 @@ __device__ __forceinline__ void warp_potrf32_v2(double* S, double* xd, double* L
 #pragma unroll
     for (int j = 0; j < LB; j++) {
         const double d = __shfl_sync(FULL, a[j], j);
-        if (!(d > 0.0)) bad |= (d != d) ? 2 : 1;
+        if (!(d > 0.0) && bad == 0) bad = (d != d) ? 2 : 1;  // the first failing pivot decides
         double rs = rsqrt(d);
         double l = d * rs;
         l = fma(fma(-l, l, d), 0.5 * rs, l);   // sqrt(d), one Newton step on top of d * rsqrt(d)
@@ -447,7 +447,7 @@ leaf_potrf_trinv_v2_kernel(double* A, int ld, int kb, double* M, double* logdet_
         }
         if (warp == 0 && lane == 0) {
             logdet_part[kb] = log(mant) + (double)esum * 0.6931471805599453;
-            if (bad) atomicOr(info, bad);
+            if (bad && *info == 0) atomicOr(info, bad);  // leaves run in sequence: an earlier failure wins
         }
     }
     __syncthreads();

@@ -41,50 +41,69 @@ def acquisition_table_argmax(model, table_x, best_values: Sequence[float], cost_
     ``(best_score, index_in_source_major_order, order)`` where ``order`` maps that position back to a row of
     ``table_x``; with ``return_scores`` the source-major score vector of THIS rank's chunk is appended.
     """
-    x = torch.as_tensor(np.asarray(table_x), dtype=torch.float64)
+    x = np.asarray(table_x, dtype=np.float64)
     n_src = len(best_values)
-    src = x[:, -1].round().to(torch.int64)
-    order = torch.argsort(src, stable=True)
-    order = order[(src[order] >= 0) & (src[order] < n_src)]
-    xs = x[order]
-    src_sorted = src[order].numpy().astype(np.int32)
-    m = xs.shape[0]
+    src = np.rint(x[:, -1]).astype(np.int64)
+    # stable source-major order without a comparison sort: the positions of every source, concatenated
+    per_src = [np.flatnonzero(src == s) for s in range(n_src)]
+    order = np.concatenate(per_src) if n_src > 0 else np.zeros(0, dtype=np.int64)
+    bounds = np.concatenate([[0], np.cumsum([len(v) for v in per_src])])
+    m = int(order.shape[0])
     kinds = list(kinds) if kinds is not None else ["HF"] + ["LF"] * (n_src - 1)
     eng = model._ensure_factor()
+    cols = model._quant_columns()
+    has_lvl = eng.dz > 0
 
-    # level / mean indices exactly as model.predict would derive them for each per-source slice
-    lvl = np.zeros(m, dtype=np.int32) if eng.dz > 0 else None
+    # this rank's contiguous chunk of the source-major sequence; only its rows are gathered and prepared
+    lo, hi = parallel.shard_range(m)
+    mc = max(hi - lo, 0)
+    lvl = np.zeros(mc, dtype=np.int32) if has_lvl else None
     mean_idx = None
-    bounds = np.searchsorted(src_sorted, np.arange(n_src + 1))
+    xq = np.zeros((mc, len(cols)))
+    xq_t = torch.from_numpy(xq)
+    xt = torch.from_numpy(x)
+    cols_t = torch.as_tensor(cols, dtype=torch.int64)
+    cost_idx = np.zeros(mc, dtype=np.int32)
     for s in range(n_src):
-        lo, hi = int(bounds[s]), int(bounds[s + 1])
-        if hi <= lo:
+        a, b = max(int(bounds[s]), lo), min(int(bounds[s + 1]), hi)
+        if b <= a:
             continue
-        part = xs[lo:hi]
-        if lvl is not None:
-            lvl[lo:hi] = model._level_index(part, False)  # QUIRK: eval-mode setlevels acts per slice (gp_plus.py:1081)
+        rows = order[a:b]
+        part = xt.index_select(0, torch.from_numpy(rows))  # multi-threaded row gather
+        cost_idx[a - lo:b - lo] = s
+        if len(cols) > 0:
+            torch.index_select(part, 1, cols_t, out=xq_t[a - lo:b - lo])
+        if has_lvl:
+            # QUIRK: eval-mode setlevels ranks the categorical columns of each per-source slice (gp_plus.py:1081);
+            # the labels come from the WHOLE slice so that a chunk of it is ranked identically
+            labels = _slice_labels(model, x, per_src[s])
+            lvl[a - lo:b - lo] = model._level_index(part, False, relevel_labels=labels)
         mi = model._mean_index(part)
         if mi is not None:
             if mean_idx is None:
-                mean_idx = np.zeros(m, dtype=np.int32)
-            mean_idx[lo:hi] = mi
-    cols = model._quant_columns()
-    xq = np.ascontiguousarray(xs[:, cols].numpy()) if len(cols) > 0 else np.zeros((m, 0))
+                mean_idx = np.zeros(mc, dtype=np.int32)
+            mean_idx[a - lo:b - lo] = mi
 
-    lo, hi = parallel.shard_range(m)
-    if hi > lo:
+    if mc > 0:
         res = eng.acq_argmax(
-            xq[lo:hi], src_sorted[lo:hi], cost=list(cost_by_source), kind_by_cost=[_KIND[k] for k in kinds],
-            best_f=list(best_values), level_idx=None if lvl is None else lvl[lo:hi],
-            mean_idx=None if mean_idx is None else mean_idx[lo:hi], maximize=maximize, si=si,
+            xq, cost_idx, cost=list(cost_by_source), kind_by_cost=[_KIND[k] for k in kinds],
+            best_f=list(best_values), level_idx=lvl, mean_idx=mean_idx, maximize=maximize, si=si,
             y_min=float(model.y_min), y_std=float(model.y_std), return_scores=return_scores)
         score, idx = res[0], int(res[1]) + lo
     else:
         res, score, idx = (None, None, np.zeros(0)), -np.inf, -1
     score, idx = parallel.global_argmax(score, idx)
     if return_scores:
-        return score, idx, order.numpy(), res[2]
-    return score, idx, order.numpy()
+        return score, idx, order, res[2]
+    return score, idx, order
+
+
+def _slice_labels(model, x: np.ndarray, rows: np.ndarray):
+    """Unique values (as int64) of every categorical column over the rows of one per-source slice."""
+    if model._level_strides is None:
+        return None
+    cols = model.qual_kernel_columns[-1]
+    return [np.unique(x[rows, c].astype(np.int64)) for c in cols]
 
 
 def BO(Xtrain=None, ytrain=None, costs=None, l_bound=None, u_bound=None, xmean=None, xstd=None, qual_index=None,

@@ -250,22 +250,40 @@ class GP_Plus(GPR):
     def _quant_kernel(self):
         return self._quant
 
-    def _level_index(self, x: torch.Tensor, training: bool) -> Optional[np.ndarray]:
+    def _level_index(self, x: torch.Tensor, training: bool, relevel_labels=None) -> Optional[np.ndarray]:
         """Row of the level-combination table per point (perm_dict lookup, gp_plus.py:1085) -- vectorised
-        mixed-radix index, identical to the itertools.product order of ``zeta_matrix``."""
+        mixed-radix index, identical to the itertools.product order of ``zeta_matrix``.
+
+        ``relevel_labels`` (one sorted array of unique values per categorical column) replaces the eval-mode
+        ``setlevels`` ranking computed from ``x`` itself: callers that score a slice of a larger batch pass the
+        labels of the whole batch so that the slice is ranked exactly as the reference would rank the batch."""
         if self._level_strides is None:
             return None
         cols = self.qual_kernel_columns[-1]
-        cat = x[:, cols].clone().type(torch.int64)
-        if not training and self.relevel_on_predict:
-            cat = torch.as_tensor(setlevels(cat)).type(torch.int64)
+        if not training and self.relevel_on_predict and relevel_labels is not None:
+            raw = x[:, cols].detach().cpu().numpy()
+            c = np.stack([np.searchsorted(np.asarray(relevel_labels[k]), raw[:, k]) for k in range(len(cols))],
+                         axis=1).astype(np.int64)
+        else:
+            cat = x[:, cols].clone().type(torch.int64)
+            if not training and self.relevel_on_predict:
+                cat = torch.as_tensor(setlevels(cat)).type(torch.int64)
+            c = cat.cpu().numpy()
         levels, strides = self._level_strides
-        c = cat.cpu().numpy()
         if (c < 0).any() or (c >= levels[None, :]).any():
             raise ValueError("The categorical input (or source indices) are not defined properly. They should be "
                              "integer values starting from zero. To solve the issue, you can use the 'setlevels' "
                              "function, which is a preprocessing function.")
         return (c * strides[None, :]).sum(1).astype(np.int32)
+
+    def _relevel_labels(self, x: torch.Tensor):
+        """Sorted unique values of every categorical column of ``x`` truncated to int64 (what eval-mode
+        ``setlevels`` would rank by), or None when the model has no categorical input."""
+        if self._level_strides is None:
+            return None
+        cols = self.qual_kernel_columns[-1]
+        cat = x[:, cols].detach().cpu().type(torch.int64).numpy()
+        return [np.unique(cat[:, k]) for k in range(len(cols))]
 
     def _latent_table(self) -> Optional[torch.Tensor]:
         if self._level_strides is None:

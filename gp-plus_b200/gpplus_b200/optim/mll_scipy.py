@@ -77,6 +77,7 @@ class MLLObjective:
         self.add_prior = add_prior
         self.regularization_parameter = regularization_parameter
         self.param_shapes = OrderedDict()
+        self._fast = None
         for n, p in self.model.named_parameters():
             if p.requires_grad:
                 self.param_shapes[n] = p.size() if len(p.size()) > 0 else torch.Size([1])
@@ -107,6 +108,25 @@ class MLLObjective:
         with torch.no_grad():
             for n, v in self.unpack_parameters(x).items():
                 params[n].copy_(v.reshape(params[n].shape))
+
+    def enable_fast_path(self) -> bool:
+        """Compile the closed-form host path (optim/_fast_objective.py) for this model and validate it against
+        the torch path; returns False (and keeps the torch path) when the model is outside its closed forms."""
+        from . import _fast_objective as FO
+        self._fast = None
+        if os.environ.get("GPPLUS_FAST_OBJECTIVE", "1") == "0":
+            return False
+        fast = FO.build(self.model, self.add_prior, self.regularization_parameter)
+        if fast is not None and FO.self_check(self, fast):
+            self._fast = fast
+        return self._fast is not None
+
+    def fun_fast(self, x: np.ndarray, return_grad=True) -> Union[float, Tuple[float, np.ndarray]]:
+        """Same value and gradient as ``fun`` without touching the module tree (restart workers only: the
+        model's parameters are NOT updated; ``fit_model_scipy`` loads the best theta at the end)."""
+        eng = self.model._get_engine()
+        self.model._factor_key = None
+        return self._fast.fun(x, lambda hyper, want: eng.mll_grad(hyper, want_grad=want), return_grad)
 
     def fun(self, x: np.ndarray, return_grad=True) -> Union[float, Tuple[float, np.ndarray]]:
         self._load(x)
@@ -161,9 +181,10 @@ def _fit_model_from_state(likobj, theta0, jac, options, method="trust-constr", c
         raise NotImplementedError("the reference's nonlinear latent constraint reads model.nn_model, which GP_Plus "
                                   "does not define (optim/mll_scipy.py:141-147); it is not part of the engine path")
     box = Bounds(lo, hi) if bounds is True else None
+    objective = likobj.fun_fast if getattr(likobj, "_fast", None) is not None else likobj.fun
     try:
         with gptsettings.fast_computations(log_prob=False):
-            return minimize(fun=likobj.fun, x0=theta0, args=(True) if jac else (False), method=method, jac=jac,
+            return minimize(fun=objective, x0=theta0, args=(True) if jac else (False), method=method, jac=jac,
                             bounds=box, constraints=[], options=options)
     except Exception as e:
         if isinstance(e, (NotPSDError, NanError)):
@@ -268,6 +289,7 @@ def fit_model_scipy(
 
     _engine.load_library()  # fail loudly before any work if the CUDA extension is missing
     likobj = MLLObjective(model, add_prior, regularization_parameter)
+    likobj.enable_fast_path()
 
     if theta0_list is None:
         theta0_list = [likobj.pack_parameters()]
