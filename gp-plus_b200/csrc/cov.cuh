@@ -93,10 +93,11 @@ __global__ void prep_points_kernel(const PrepArgs a) {
 
 // r = y - m(x), diag_add = noise[group] + jitter   (means: gp_plus.py:509-544, noise: multifidelity.py:105-136)
 __global__ void prep_targets_kernel(const double* y, const int* mean_idx, const double* beta, int n_mean,
-                                    const int* noise_idx, const double* noise, int n_noise, double jitter, int n,
-                                    int np, double* r, double* diag_add) {
+                                    const int* noise_idx, const double* noise, int n_noise, double jitter,
+                                    const double* jitter_dev, int n, int np, double* r, double* diag_add) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= np) return;
+    if (jitter_dev) jitter = *jitter_dev;  // graph replays read the per-evaluation scalars from device memory
     if (i < n) {
         int mi = mean_idx ? mean_idx[i] : 0;
         double m = (n_mean > 0 && mi >= 0 && mi < n_mean) ? beta[mi] : 0.0;
@@ -123,6 +124,7 @@ struct CovArgs {
     int pad_identity;        // padded diagonal entries = 1 (training K_y)
     int dqp, dz;
     double sf2;
+    const double* sf2_dev;   // when set, overrides sf2 (CUDA-graph replays keep kernel arguments fixed)
     const double* diag_add;  // [n] added on the diagonal when same (noise + jitter) or NULL
     const double* alpha;     // optional [cols]: mean_part[tj*ld_part + row] = sum_col K[row,col]*alpha[col]
     double* mean_part;
@@ -211,7 +213,7 @@ __global__ void __launch_bounds__(COV_THREADS) cov_tile_kernel(const CovArgs a) 
     tile_cross_dmma(Xi, Xj, dqp, wm0, wn0, g, t, acc);
 
     const bool diag_tile = a.same && (ti == tj);
-    const double sf2 = a.sf2;
+    const double sf2 = a.sf2_dev ? *a.sf2_dev : a.sf2;
     double* outp = a.out + (long long)ti * CT * a.ld + (long long)tj * CT;
 #pragma unroll
     for (int mi = 0; mi < 4; mi++) {
@@ -281,6 +283,7 @@ struct GradArgs {
     int n, np, T;
     int dq, dqp, dz;
     double sf2;
+    const double* sf2_dev;  // when set, overrides sf2
     double* tile_part;  // [ntiles * (1 + dqp)]: sum W*Kc, sum Q*dx_d^2 (d < dq)
     double* zpart;      // [T * np * ZP]: slot (t, p): partial of sum_j P_pj (z_p - z_j)
 };
@@ -340,7 +343,7 @@ __global__ void __launch_bounds__(COV_THREADS) grad_tile_kernel(const GradArgs a
     tile_cross_dmma(Xi, Xj, dqp, wm0, wn0, g, t, acc);
 
     const bool diag_tile = (ti == tj);
-    const double sf2 = a.sf2;
+    const double sf2 = a.sf2_dev ? *a.sf2_dev : a.sf2;
     const double* Wp = a.Kinv + (long long)ti * CT * a.ld + (long long)tj * CT;
 
     double sumWK = 0.0;

@@ -23,7 +23,11 @@ namespace gpp {
 
 // process-wide count of kernel launches issued by this library (reported by gpp_launch_count)
 inline std::atomic<long long> g_launches{0};
-inline void count_launch(int k = 1) { g_launches.fetch_add(k, std::memory_order_relaxed); }
+inline thread_local long long t_launches = 0;  // same count per host thread (graph-capture accounting)
+inline void count_launch(int k = 1) {
+    g_launches.fetch_add(k, std::memory_order_relaxed);
+    t_launches += k;
+}
 
 constexpr int TILE = 128;        // output tile edge and K block
 constexpr int BK = 16;           // k-chunk staged per pipeline stage

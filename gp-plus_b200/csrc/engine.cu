@@ -15,6 +15,7 @@
 
 #include "chol.cuh"
 #include "cov.cuh"
+#include "objective.h"
 #include "predict.cuh"
 #include "solve.cuh"
 
@@ -90,14 +91,24 @@ struct gpp_handle {
     gpp_timings tm;
     CholLookahead la;
     bool use_lookahead = true;
+    // CUDA-graph replay of one whole evaluation (small problems are launch-bound): [want_grad]
+    cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
+    long long graph_kernels[2] = {0, 0};
+    bool use_graph = false;
+    bool capturing = false;
+    ThetaLayout layout;                            // optional: O(p) host side of MLLObjective.fun
+    std::vector<double> g_w, g_z, g_noise, g_beta;  // gradient scratch of gpp_objective
 };
 
 static const double* hyp_w(const gpp_handle* h) { return h->hyp; }
 static const double* hyp_z(const gpp_handle* h) { return h->hyp + h->dq; }
 static const double* hyp_noise(const gpp_handle* h) { return h->hyp + h->dq + h->n_combo * h->dz; }
 static const double* hyp_beta(const gpp_handle* h) { return h->hyp + h->dq + h->n_combo * h->dz + h->n_noise; }
+// per-evaluation scalars live behind the vectors so that graph replays need no new kernel arguments
+static const double* hyp_sf2(const gpp_handle* h) { return hyp_beta(h) + h->n_mean; }
+static const double* hyp_jitter(const gpp_handle* h) { return hyp_beta(h) + h->n_mean + 1; }
 
-extern "C" int gpp_version(void) { return 100; }
+extern "C" int gpp_version(void) { return 101; }
 
 extern "C" int gpp_device_count(void) {
     int c = 0;
@@ -133,6 +144,8 @@ extern "C" void gpp_destroy(gpp_handle* h) {
     if (h->res_host) cudaFreeHost(h->res_host);
     if (h->gz_host) cudaFreeHost(h->gz_host);
     for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(h->ev[i]);
+    for (int i = 0; i < 2; i++)
+        if (h->graph_exec[i]) cudaGraphExecDestroy(h->graph_exec[i]);
     h->la.destroy();
     if (h->st) cudaStreamDestroy(h->st);
     delete h;
@@ -190,6 +203,14 @@ extern "C" int gpp_create(const gpp_problem* p, int device, gpp_handle** out) {
         }                         \
     } while (0)
 
+    {
+        // optional: sleep instead of spinning in cudaStreamSynchronize (many restart workers per GPU); must be
+        // set before the context is created, so it only takes effect for the first handle of a process
+        const char* e = getenv("GPP_BLOCKING_SYNC");
+        if (e && atoi(e) != 0) {
+            if (cudaSetDeviceFlags(cudaDeviceScheduleBlockingSync) != cudaSuccess) cudaGetLastError();
+        }
+    }
     CKH(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
     for (int i = 0; i < EV_COUNT; i++) CKH(cudaEventCreate(&h->ev[i]));
     CKH(chol_set_attributes());
@@ -200,6 +221,8 @@ extern "C" int gpp_create(const gpp_problem* p, int device, gpp_handle** out) {
         if ((e = getenv("GPP_CHOL")) != nullptr) h->use_lookahead = strcmp(e, "blocked") != 0;
         if ((e = getenv("GPP_LEAF")) != nullptr) g_leaf_version = atoi(e) == 1 ? 1 : 2;
         if ((e = getenv("GPP_GEMM_BM")) != nullptr) g_gemm_bm = atoi(e) == 64 ? 64 : 128;
+        h->use_graph = h->T <= 16;  // N <= 2048: an evaluation is a chain of ~25-100 tiny launches
+        if ((e = getenv("GPP_GRAPH")) != nullptr) h->use_graph = atoi(e) != 0;
     }
     CKH(h->la.init(h->T));
 
@@ -255,7 +278,7 @@ extern "C" int gpp_create(const gpp_problem* p, int device, gpp_handle** out) {
         return rc;
     }
 
-    h->hyp_len = h->dq + h->n_combo * h->dz + h->n_noise + h->n_mean;
+    h->hyp_len = h->dq + h->n_combo * h->dz + h->n_noise + h->n_mean + 2;
     CKH(dev_alloc(&h->hyp, (size_t)h->hyp_len));
     CKH(cudaMallocHost((void**)&h->hyp_host, sizeof(double) * std::max(h->hyp_len, 1)));
     CKH(dev_alloc(&h->xs, (size_t)np * h->dqp));
@@ -289,6 +312,7 @@ extern "C" int gpp_create(const gpp_problem* p, int device, gpp_handle** out) {
 }
 
 static void mark(gpp_handle* h, int which) {
+    if (h->capturing) return;  // timing events cannot live inside a captured graph
     cudaEventRecord(h->ev[which], h->st);
     h->ev_valid[which] = true;
 }
@@ -312,17 +336,22 @@ static int check_hyper(const gpp_handle* h, const gpp_hyper* hy) {
     return GPP_OK;
 }
 
-// upload hyper-parameters and prepare the per-point panels of the training set
-static int stage_prep(gpp_handle* h, const gpp_hyper* hy, double jitter) {
+// hyper-parameters of this evaluation into the pinned staging buffer
+static void fill_hyper_host(gpp_handle* h, const gpp_hyper* hy, double jitter) {
     double* hh = h->hyp_host;
     int o = 0;
     for (int d = 0; d < h->dq; d++) hh[o++] = hy->w[d];
     for (int k = 0; k < h->n_combo * h->dz; k++) hh[o++] = hy->z[k];
     for (int k = 0; k < h->n_noise; k++) hh[o++] = hy->noise[k];
     for (int k = 0; k < h->n_mean; k++) hh[o++] = hy->beta[k];
+    hh[o++] = hy->sigma_f2;
+    hh[o++] = jitter;
     h->sf2 = hy->sigma_f2;
-    if (h->hyp_len > 0)
-        CK(cudaMemcpyAsync(h->hyp, hh, sizeof(double) * h->hyp_len, cudaMemcpyHostToDevice, h->st));
+}
+
+// upload the staged hyper-parameters and prepare the per-point panels of the training set
+static int stage_prep(gpp_handle* h) {
+    CK(cudaMemcpyAsync(h->hyp, h->hyp_host, sizeof(double) * h->hyp_len, cudaMemcpyHostToDevice, h->st));
     PrepArgs pa;
     pa.xq = h->xq;
     pa.level_idx = h->level_idx;
@@ -343,14 +372,15 @@ static int stage_prep(gpp_handle* h, const gpp_hyper* hy, double jitter) {
     CK(cudaGetLastError());
     count_launch();
     prep_targets_kernel<<<nb, 256, 0, h->st>>>(h->y, h->mean_idx, hyp_beta(h), h->n_mean, h->noise_idx, hyp_noise(h),
-                                                h->n_noise, jitter, (int)h->n, (int)h->np, h->r, h->diag_add);
+                                                h->n_noise, 0.0, hyp_jitter(h), (int)h->n, (int)h->np, h->r,
+                                                h->diag_add);
     CK(cudaGetLastError());
     count_launch();
     return GPP_OK;
 }
 
-// K_y (lower tiles) into A, then A -> L in place, diagonal blocks of M <- L_kk^-1; returns potrf info
-static int stage_factor(gpp_handle* h, int* info_out) {
+// K_y (lower tiles) into A, then A -> L in place, diagonal blocks of M <- L_kk^-1 (status in h->info)
+static int stage_factor(gpp_handle* h) {
     CK(cudaMemsetAsync(h->info, 0, sizeof(int), h->st));
     CovArgs ca;
     memset(&ca, 0, sizeof(ca));
@@ -367,6 +397,7 @@ static int stage_factor(gpp_handle* h, int* info_out) {
     ca.dqp = h->dqp;
     ca.dz = h->dz;
     ca.sf2 = h->sf2;
+    ca.sf2_dev = hyp_sf2(h);
     ca.diag_add = h->diag_add;
     CK(launch_cov(ca, h->kernel, h->st));
     mark(h, EV_COV);
@@ -375,9 +406,6 @@ static int stage_factor(gpp_handle* h, int* info_out) {
     else
         CK(potrf_blocked(h->A, h->M, (int)h->np, h->T, h->logdet_part, h->info, h->st));
     mark(h, EV_CHOL);
-    CK(cudaMemcpyAsync(h->info_host, h->info, sizeof(int), cudaMemcpyDeviceToHost, h->st));
-    CK(cudaStreamSynchronize(h->st));
-    *info_out = *h->info_host;
     return GPP_OK;
 }
 
@@ -416,6 +444,7 @@ static int stage_grad(gpp_handle* h) {
     ga.dqp = h->dqp;
     ga.dz = h->dz;
     ga.sf2 = h->sf2;
+    ga.sf2_dev = hyp_sf2(h);
     ga.tile_part = h->tile_part;
     ga.zpart = h->zpart;
     CK(launch_grad(ga, h->kernel, h->st));
@@ -456,23 +485,71 @@ static int stage_finish(gpp_handle* h, int want_grad) {
     CK(cudaGetLastError());
     count_launch();
     CK(cudaMemcpyAsync(h->res_host, h->res, sizeof(double) * h->res_len, cudaMemcpyDeviceToHost, h->st));
-    mark(h, EV_END);
-    CK(cudaStreamSynchronize(h->st));
     return GPP_OK;
 }
 
 static const double kJitter[4] = {0.0, 1e-8, 1e-7, 1e-6};  // psd_safe_cholesky ladder
 
-// factor K_y with the jitter ladder; on success L is in A and diag blocks of M are inverted
-static int factor_with_ladder(gpp_handle* h, const gpp_hyper* hy) {
+// every device operation of one evaluation, in stream order, without host synchronisation
+static int enqueue_eval(gpp_handle* h, int want_grad) {
+    int rc;
+    if ((rc = stage_prep(h)) != GPP_OK) return rc;
+    if ((rc = stage_factor(h)) != GPP_OK) return rc;
+    if ((rc = stage_inverse_solve(h)) != GPP_OK) return rc;
+    if (want_grad && (rc = stage_grad(h)) != GPP_OK) return rc;
+    return stage_finish(h, want_grad);
+}
+
+// capture enqueue_eval once per (handle, want_grad); returns false when capture is not possible
+static bool ensure_graph(gpp_handle* h, int want_grad) {
+    const int slot = want_grad ? 1 : 0;
+    if (h->graph_exec[slot]) return true;
+    if (cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    const long long k0 = t_launches;
+    h->capturing = true;
+    const int rc = enqueue_eval(h, want_grad);
+    h->capturing = false;
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(h->st, &g);
+    const long long kernels = t_launches - k0;  // launches issued by THIS thread while capturing
+    g_launches.fetch_sub(kernels);              // captured, not executed
+    if (rc != GPP_OK || e != cudaSuccess || !g) {
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        return false;
+    }
+    cudaGraphExec_t ex = nullptr;
+    e = cudaGraphInstantiate(&ex, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess || !ex) {
+        cudaGetLastError();
+        return false;
+    }
+    h->graph_exec[slot] = ex;
+    h->graph_kernels[slot] = kernels;
+    return true;
+}
+
+// one evaluation with the jitter ladder; on success L is in A, L^-1 in M, alpha / res_host are valid
+static int run_eval(gpp_handle* h, const gpp_hyper* hy, int want_grad) {
     for (int a = 0; a < 4; a++) {
         for (int i = 0; i < EV_COUNT; i++) h->ev_valid[i] = false;
+        fill_hyper_host(h, hy, kJitter[a]);
+        if (h->use_graph && !ensure_graph(h, want_grad)) h->use_graph = false;
         mark(h, EV_START);
-        int rc = stage_prep(h, hy, kJitter[a]);
-        if (rc != GPP_OK) return rc;
-        int info = 0;
-        rc = stage_factor(h, &info);
-        if (rc != GPP_OK) return rc;
+        if (h->use_graph) {
+            CK(cudaGraphLaunch(h->graph_exec[want_grad ? 1 : 0], h->st));
+            count_launch((int)h->graph_kernels[want_grad ? 1 : 0]);
+        } else {
+            int rc = enqueue_eval(h, want_grad);
+            if (rc != GPP_OK) return rc;
+        }
+        mark(h, EV_END);
+        CK(cudaStreamSynchronize(h->st));
+        const int info = (int)h->res_host[2];
         if (info & 2) {
             g_err = "NaN encountered while factorising K_y";
             return GPP_ERR_NAN;
@@ -492,11 +569,8 @@ extern "C" int gpp_mll_grad(gpp_handle* h, const gpp_hyper* hy, int want_grad, g
     if (rc != GPP_OK) return rc;
     CK(cudaSetDevice(h->device));
     h->factorized = false;
-    rc = factor_with_ladder(h, hy);
+    rc = run_eval(h, hy, want_grad ? 1 : 0);
     if (rc != GPP_OK) return rc;
-    if ((rc = stage_inverse_solve(h)) != GPP_OK) return rc;
-    if (want_grad && (rc = stage_grad(h)) != GPP_OK) return rc;
-    if ((rc = stage_finish(h, want_grad)) != GPP_OK) return rc;
     h->factorized = true;
 
     const double* r = h->res_host;
@@ -538,6 +612,58 @@ extern "C" int gpp_mll_grad(gpp_handle* h, const gpp_hyper* hy, int want_grad, g
     return GPP_OK;
 }
 
+extern "C" int gpp_set_theta_layout(gpp_handle* h, const gpp_theta_layout* layout) {
+    if (!h || !layout) ARG_FAIL("gpp_set_theta_layout: null argument");
+    const char* err = layout_copy(h->layout, layout, h->dq, h->dz, h->n_combo, h->n_noise, h->n_mean);
+    if (err) {
+        h->layout.set = false;
+        ARG_FAIL(err);
+    }
+    h->g_w.assign(std::max(h->dq, 1), 0.0);
+    h->g_z.assign(std::max(h->n_combo * h->dz, 1), 0.0);
+    h->g_noise.assign(std::max(h->n_noise, 1), 0.0);
+    h->g_beta.assign(std::max(h->n_mean, 1), 0.0);
+    return GPP_OK;
+}
+
+extern "C" int gpp_objective(gpp_handle* h, const double* theta, int want_grad, double* value, double* grad,
+                             gpp_mll_result* detail) {
+    if (!h || !theta || !value) ARG_FAIL("gpp_objective: null argument");
+    if (!h->layout.set) ARG_FAIL("gpp_objective: call gpp_set_theta_layout first");
+    if (want_grad && !grad) ARG_FAIL("gpp_objective: grad missing");
+    ThetaLayout& L = h->layout;
+    layout_natural(L, theta, h->dq, h->dz, h->n_combo, h->n_noise, h->n_mean);
+    gpp_hyper hy;
+    hy.w = L.w.data();
+    hy.z = h->dz > 0 ? L.z.data() : nullptr;
+    hy.sigma_f2 = L.sf2;
+    hy.noise = L.noise.data();
+    hy.beta = h->n_mean > 0 ? L.beta.data() : nullptr;
+    gpp_mll_result r;
+    memset(&r, 0, sizeof(r));
+    r.d_w = h->g_w.data();
+    r.d_z = h->g_z.data();
+    r.d_noise = h->g_noise.data();
+    r.d_beta = h->g_beta.data();
+    int rc = gpp_mll_grad(h, &hy, want_grad, &r);
+    if (rc != GPP_OK) return rc;
+    if (want_grad) layout_chain(L, r, h->dq, h->dz, h->n_combo, h->n_noise, h->n_mean, grad);
+    const double logp = layout_priors(L, want_grad ? grad : nullptr);
+    *value = r.nll - logp;
+    if (detail) {
+        detail->nll = r.nll;
+        detail->logdet = r.logdet;
+        detail->quad = r.quad;
+        detail->jitter = r.jitter;
+        detail->d_sigma_f2 = r.d_sigma_f2;
+    }
+    if (!(*value == *value)) {
+        g_err = "NaN in the objective";
+        return GPP_ERR_NAN;
+    }
+    return GPP_OK;
+}
+
 extern "C" int gpp_get_timings(gpp_handle* h, gpp_timings* out) {
     if (!h || !out) ARG_FAIL("gpp_get_timings: null argument");
     *out = h->tm;
@@ -550,7 +676,8 @@ extern "C" int gpp_covariance(gpp_handle* h, const gpp_hyper* hy, double* k_out)
     if (rc != GPP_OK) return rc;
     CK(cudaSetDevice(h->device));
     h->factorized = false;
-    if ((rc = stage_prep(h, hy, 0.0)) != GPP_OK) return rc;
+    fill_hyper_host(h, hy, 0.0);
+    if ((rc = stage_prep(h)) != GPP_OK) return rc;
     CovArgs ca;
     memset(&ca, 0, sizeof(ca));
     ca.xs_r = ca.xs_c = h->xs;
@@ -600,10 +727,8 @@ extern "C" int gpp_factorize(gpp_handle* h, const gpp_hyper* hy) {
     if (rc != GPP_OK) return rc;
     CK(cudaSetDevice(h->device));
     h->factorized = false;
-    rc = factor_with_ladder(h, hy);
+    rc = run_eval(h, hy, 0);
     if (rc != GPP_OK) return rc;
-    if ((rc = stage_inverse_solve(h)) != GPP_OK) return rc;
-    CK(cudaStreamSynchronize(h->st));
     h->factorized = true;
     return GPP_OK;
 }

@@ -22,8 +22,10 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libg
 EXPORTS = (
     "gpp_version", "gpp_device_count", "gpp_last_error", "gpp_launch_count", "gpp_create", "gpp_destroy", "gpp_mll_grad",
     "gpp_get_timings", "gpp_covariance", "gpp_fetch", "gpp_factorize", "gpp_predict", "gpp_acq_argmax",
-    "gpp_probe_dgemm",
+    "gpp_probe_dgemm", "gpp_set_theta_layout", "gpp_objective",
 )
+
+PRIOR_NORMAL, PRIOR_LOGNORMAL_OS, PRIOR_HORSESHOE, PRIOR_MOLLIFIED, PRIOR_CONST = 0, 1, 2, 3, 4
 
 
 class NotPSDError(RuntimeError):
@@ -55,6 +57,18 @@ class _Hyper(C.Structure):
 class _MllResult(C.Structure):
     _fields_ = [("nll", C.c_double), ("logdet", C.c_double), ("quad", C.c_double), ("jitter", C.c_double),
                 ("d_sigma_f2", C.c_double), ("d_w", _dp), ("d_z", _dp), ("d_noise", _dp), ("d_beta", _dp)]
+
+
+class _Prior(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("off", C.c_int32), ("len", C.c_int32), ("a", _dp), ("b", _dp), ("c", _dp)]
+
+
+class _ThetaLayout(C.Structure):
+    _fields_ = [("p", C.c_int32), ("off_latent", C.c_int32), ("n_onehot", C.c_int32), ("zeta", _dp),
+                ("latent_const", _dp), ("latent_ls", C.c_double), ("off_noise", C.c_int32), ("noise_const", _dp),
+                ("noise_lb", C.c_double), ("off_os", C.c_int32), ("os_const", C.c_double), ("off_ls", C.c_int32),
+                ("ls_const", _dp), ("ls_kind", C.c_int32), ("w_num", C.c_double), ("off_mean", _ip),
+                ("mean_const", _dp), ("n_priors", C.c_int32), ("priors", C.POINTER(_Prior))]
 
 
 class _Timings(C.Structure):
@@ -104,6 +118,10 @@ def load_library():
         lib.gpp_acq_argmax.restype = C.c_int
         lib.gpp_probe_dgemm.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
         lib.gpp_probe_dgemm.restype = C.c_int
+        lib.gpp_set_theta_layout.argtypes = [C.c_void_p, C.POINTER(_ThetaLayout)]
+        lib.gpp_set_theta_layout.restype = C.c_int
+        lib.gpp_objective.argtypes = [C.c_void_p, C.c_void_p, C.c_int, _dp, C.c_void_p, C.POINTER(_MllResult)]
+        lib.gpp_objective.restype = C.c_int
         _lib = lib
         return lib
 
@@ -239,6 +257,67 @@ class Engine:
             if self.n_mean > 0:
                 out["d_beta"] = d_beta[: self.n_mean]
         return out
+
+    # -- objective in raw theta (the whole body of MLLObjective.fun in one GIL-free call) -----------------
+    def set_theta_layout(self, spec: Dict):
+        """``spec``: the dictionary produced by ``FastObjective.layout_spec()`` (optim/_fast_objective.py)."""
+        keep = []
+
+        def arr(a):
+            if a is None:
+                return None
+            a = _f64(a).reshape(-1)
+            keep.append(a)
+            return a.ctypes.data_as(_dp)
+
+        lay = _ThetaLayout()
+        lay.p = int(spec["p"])
+        lay.off_latent = int(spec.get("off_latent", -1))
+        lay.n_onehot = int(spec.get("n_onehot", 0))
+        lay.zeta = arr(spec.get("zeta"))
+        lay.latent_const = arr(spec.get("latent_const"))
+        lay.latent_ls = float(spec.get("latent_ls", 1.0))
+        lay.off_noise = int(spec["off_noise"])
+        lay.noise_const = arr(spec.get("noise_const"))
+        lay.noise_lb = float(spec["noise_lb"])
+        lay.off_os = int(spec["off_os"])
+        lay.os_const = float(spec.get("os_const", 0.0))
+        lay.off_ls = int(spec.get("off_ls", -1))
+        lay.ls_const = arr(spec.get("ls_const"))
+        lay.ls_kind = int(spec.get("ls_kind", 0))
+        lay.w_num = float(spec.get("w_num", 0.5))
+        om = np.ascontiguousarray(np.asarray(spec.get("off_mean", []), dtype=np.int32))
+        keep.append(om)
+        lay.off_mean = om.ctypes.data_as(_ip) if om.size else None
+        lay.mean_const = arr(spec.get("mean_const")) if om.size else None
+        pri = spec.get("priors", [])
+        parr = (_Prior * max(len(pri), 1))()
+        for i, (kind, off, length, a, b, c) in enumerate(pri):
+            parr[i].kind, parr[i].off, parr[i].len = int(kind), int(off), int(length)
+            parr[i].a, parr[i].b, parr[i].c = arr(a), arr(b), arr(c)
+        lay.n_priors = len(pri)
+        lay.priors = parr
+        rc = self._lib.gpp_set_theta_layout(self._h, C.byref(lay))
+        del keep
+        if rc != GPP_OK:
+            _raise(rc, "gpp_set_theta_layout")
+        self._p = lay.p
+        self._grad_buf = np.zeros(lay.p)
+        self._val_buf = C.c_double()
+
+    def objective(self, theta, want_grad: bool = True):
+        """(neg log posterior, gradient) at raw ``theta``; the gradient array is freshly allocated."""
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        if th.shape[0] != self._p:
+            raise ValueError("theta must have %d entries" % self._p)
+        grad = np.empty(self._p) if want_grad else None
+        rc = self._lib.gpp_objective(self._h, th.ctypes.data, 1 if want_grad else 0, C.byref(self._val_buf),
+                                     grad.ctypes.data if want_grad else None, None)
+        if rc != GPP_OK:
+            _raise(rc, "gpp_objective")
+        if want_grad:
+            return self._val_buf.value, grad
+        return self._val_buf.value
 
     def timings(self) -> Dict[str, float]:
         t = _Timings()

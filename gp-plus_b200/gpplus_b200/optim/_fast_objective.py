@@ -186,6 +186,35 @@ class FastObjective:
             else:
                 raise _Unsupported("prior type %s" % type(prior).__name__)
 
+    def layout_spec(self):
+        """The same structure as plain data for ``gpp_set_theta_layout`` (include/gpplus_b200.h)."""
+        from .. import _engine as E
+        spec = {"p": self.p, "off_noise": -1 if self.noise is None else self.noise[0], "noise_const": self.noise_const,
+                "noise_lb": self.noise_lb, "off_os": -1 if self.os is None else self.os[0], "os_const": self.os_const}
+        if hasattr(self, "zeta"):
+            spec.update(off_latent=-1 if self.lat is None else self.lat[0], n_onehot=self.n_onehot, zeta=self.zeta,
+                        latent_const=self.lat_const, latent_ls=self.lat_ls)
+        if self.dq > 0:
+            spec.update(off_ls=-1 if self.ls is None else self.ls[0], ls_const=self.ls_const,
+                        ls_kind=1 if self.ls_kind == "rough" else 0, w_num=0.0 if self.w_num is None else self.w_num)
+        if self.n_mean > 0:
+            spec.update(off_mean=[-1 if s is None else s[0] for s, _ in self.mean],
+                        mean_const=[c for _, c in self.mean])
+        pri = []
+        for kind, sl, c in self.priors:
+            if kind == "normal":
+                pri.append((E.PRIOR_NORMAL, sl[0], sl[1] - sl[0], c[0], c[1], None))
+            elif kind == "lognormal_os":
+                pri.append((E.PRIOR_LOGNORMAL_OS, -1, 1, [c[0]], [c[1]], None))
+            elif kind == "horseshoe":
+                pri.append((E.PRIOR_HORSESHOE, sl[0], sl[1] - sl[0], c[0], c[1], None))
+            elif kind == "mollified":
+                pri.append((E.PRIOR_MOLLIFIED, sl[0], sl[1] - sl[0], c[0], c[1], c[2]))
+            else:
+                pri.append((E.PRIOR_CONST, -1, 1, [c[0]], None, None))
+        spec["priors"] = pri
+        return spec
+
     # -- evaluation ----------------------------------------------------------------------------
     def natural(self, theta: np.ndarray):
         """theta (already float32-rounded, float64 storage) -> natural hyper-parameters + chain-rule factors."""

@@ -126,6 +126,11 @@ class MLLObjective:
         model's parameters are NOT updated; ``fit_model_scipy`` loads the best theta at the end)."""
         eng = self.model._get_engine()
         self.model._factor_key = None
+        if os.environ.get("GPPLUS_NATIVE_OBJECTIVE", "1") != "0":
+            if getattr(eng, "_layout_owner", None) is not self._fast:
+                eng.set_theta_layout(self._fast.layout_spec())
+                eng._layout_owner = self._fast
+            return eng.objective(x, return_grad)  # one GIL-free call: transforms, device evaluation, priors
         return self._fast.fun(x, lambda hyper, want: eng.mll_grad(hyper, want_grad=want), return_grad)
 
     def fun(self, x: np.ndarray, return_grad=True) -> Union[float, Tuple[float, np.ndarray]]:

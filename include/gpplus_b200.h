@@ -157,6 +157,54 @@ int gpp_acq_argmax(gpp_handle* h, int64_t m, const double* xq, const int32_t* le
                    int maximize, double si, double y_min, double y_std, double min_var,
                    double* scores, double* best_score, int64_t* best_index);
 
+/* ---- the O(p) host side of MLLObjective.fun inside the library --------------------------------
+ * gpp_objective(theta) = -( log N(y; m, K_y) + sum log-priors ) and its gradient w.r.t. the RAW parameter
+ * vector theta that scipy optimises -- the whole body of MLLObjective.fun (optim/mll_scipy.py:112-127:
+ * float32 cast of theta :97, raw->natural transforms, marginal_log_likelihood :37-47, backward :123,
+ * pack_grads :101-110) in one call that holds no Python lock.  The layout is compiled from the model by
+ * gpplus_b200/optim/_fast_objective.py and checked there against the torch path.
+ *   ls_kind 0: lengthscale = exp(raw) (gpytorch Positive(exp));  1: 2^-1/2 * 10^(-raw/2) (models/gp_plus.py:252)
+ *   w_num 0.5 / 1.0: w = w_num / lengthscale^2 (RBF / Matern families);  0: w = lengthscale (kernels/Rough_RBF.py)
+ * Offsets index theta; a negative offset means "frozen": the *_const value is used and no gradient is written. */
+#define GPP_PRIOR_NORMAL 0        /* raw parameters:   a = loc[len], b = scale[len]                      */
+#define GPP_PRIOR_LOGNORMAL_OS 1  /* CONSTRAINED outputscale (gpregression.py:113-115): a[0]=loc, b[0]=scale */
+#define GPP_PRIOR_HORSESHOE 2     /* raw noise:        a = scale[len], b = lb[len]  (priors/horseshoe.py:60-66) */
+#define GPP_PRIOR_MOLLIFIED 3     /* raw lengthscale:  a = lo[len], b = hi[len], c = tail_sigma[len]       */
+#define GPP_PRIOR_CONST 4         /* frozen parameter: a[0] = its constant log-density                     */
+
+typedef struct gpp_prior {
+    int32_t kind, off, len;
+    const double *a, *b, *c;
+} gpp_prior;
+
+typedef struct gpp_theta_layout {
+    int32_t p;                  /* length of theta */
+    int32_t off_latent;         /* A [dz x n_onehot] row-major (nn.Linear weight, models/gp_plus.py:1245-1247) */
+    int32_t n_onehot;
+    const double* zeta;         /* [n_combo x n_onehot] one-hot table (models/gp_plus.py:1027-1073) */
+    const double* latent_const; /* [dz x n_onehot] when off_latent < 0 */
+    double latent_ls;           /* fixed lengthscale of the latent RBF kernel (models/gp_plus.py:223-226) */
+    int32_t off_noise;          /* raw_noise [n_noise]; noise = noise_lb + exp(raw) */
+    const double* noise_const;
+    double noise_lb;
+    int32_t off_os;             /* raw_outputscale; sigma_f^2 = softplus(raw) */
+    double os_const;
+    int32_t off_ls;             /* raw_lengthscale [dq] */
+    const double* ls_const;
+    int32_t ls_kind;
+    double w_num;
+    const int32_t* off_mean;    /* [n_mean] offsets of the mean constants */
+    const double* mean_const;   /* [n_mean] */
+    int32_t n_priors;
+    const gpp_prior* priors;    /* evaluated in this order (named_priors order) */
+} gpp_theta_layout;
+
+/* copies the layout (and every array it points to) into the handle */
+int gpp_set_theta_layout(gpp_handle* h, const gpp_theta_layout* layout);
+/* value = neg log posterior at theta[p]; grad[p] may be NULL when want_grad == 0; detail may be NULL */
+int gpp_objective(gpp_handle* h, const double* theta, int want_grad, double* value, double* grad,
+                  gpp_mll_result* detail);
+
 /* FP64 DMMA GEMM probe used by bench/selftest: C[m x n] = A[m x k] * B[n x k]^T on device
  * scratch, returns average milliseconds per launch over iters (m,n,k multiples of 128). */
 int gpp_probe_dgemm(int device, int m, int n, int k, int iters, float* ms_out);

@@ -177,3 +177,20 @@ def test_fused_table_acquisition_matches_slice_by_slice_reference_sequence():
         assert np.allclose(got, ref_scores, rtol=1e-9, atol=1e-14)
         assert abs(score - ref_scores[ref_index]) <= 1e-9 * abs(ref_scores[ref_index])
         assert np.array_equal(table[order][:, -1], np.sort(table[:, -1]))
+
+
+@pytest.mark.parametrize("maker", [_c1, _c2, lambda: _c2("Matern52Kernel"), _c3])
+def test_native_objective_equals_torch_path(maker):
+    """gpp_objective (float32 cast, transforms, priors, chain rule inside the library) == MLLObjective.fun."""
+    from gpplus_b200.optim.mll_scipy import MLLObjective, _sample_from_prior
+    m, spec, _, _ = maker()
+    obj = MLLObjective(m, True, [0, 0])
+    assert obj.enable_fast_path()
+    torch.manual_seed(1)
+    thetas = [obj.pack_parameters()] + [np.clip(_sample_from_prior(m), -6, 4) for _ in range(3)]
+    for th in thetas:
+        f_ref, g_ref = obj.fun(th)
+        f, g = obj.fun_fast(th)
+        assert abs(f - f_ref) <= 1e-10 * max(1.0, abs(f_ref))
+        assert np.max(np.abs(g - g_ref)) <= 1e-9 * max(1.0, np.max(np.abs(g_ref)))
+        assert isinstance(obj.fun_fast(th, False), float)
