@@ -27,7 +27,8 @@ constexpr int LB = 32;     // sub-block edge inside a 128x128 leaf
 constexpr int LLD = 132;   // smem leading dimension: 132 = 4 (mod 16) keeps every DMMA fragment load conflict-free
 constexpr int TLD = 36;    // per-warp scratch leading dimension (same residue)
 constexpr int LEAF_SMEM_BYTES = (TILE * LLD + TILE + 3 * LB * TLD) * 8;
-constexpr int PANEL_BLOCKS = 4;
+constexpr int PANEL_BLOCKS = 4;   // leaf-level panel: in-panel updates run at K = 128
+inline int g_panel_blocks = 0;     // look-ahead panel width in 128-columns; 0 = by size (8 from N = 12288, else 4)
 constexpr unsigned FULL = 0xffffffffu;
 
 // C(32x32) += A(32x32) * B(32x32) by one warp on DMMA; A(r,k) and B(k,n) are element getters.
@@ -357,6 +358,125 @@ __device__ __forceinline__ void warp_trinv32_v2(const double* S, const double* x
     }
 }
 
+
+// Third-generation 32x32 diagonal factorisation: four columns at a time.  The 4x4 pivot block is broadcast by
+// shuffle and factored redundantly by every lane (no communication inside the micro-panel), each lane then
+// solves its own row against it, and one shared-memory exchange per micro-panel feeds the rank-4 update of the
+// remaining columns.  Updates are not predicated: entries above the diagonal hold bounded garbage that is
+// never read.  ~1400 instructions per block instead of ~4100, 8 exchanges instead of 32.
+#define GPP_PIVOT(d, rs, l)                                       \
+    if (!((d) > 0.0) && bad == 0) bad = ((d) != (d)) ? 2 : 1;     \
+    rs = rsqrt(d);                                                \
+    l = (d) * rs;                                                 \
+    l = fma(fma(-l, l, (d)), 0.5 * rs, l);                        \
+    rs = fma(fma(-l, rs, 1.0), rs, rs);
+
+__device__ __forceinline__ void warp_potrf32_v3(double* S, double* xd, double* LT, int b, int lane, int& bad,
+                                                double& mant, int& esum) {
+    double a[LB];
+    double* row = S + (b + lane) * LLD + b;
+#pragma unroll
+    for (int k = 0; k < LB; k += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(row + k);
+        a[k] = (k <= lane) ? v.x : 0.0;
+        a[k + 1] = (k + 1 <= lane) ? v.y : 0.0;
+    }
+    double mydinv = 0.0;
+#pragma unroll
+    for (int c0 = 0; c0 < LB; c0 += 4) {
+        const double p00 = __shfl_sync(FULL, a[c0], c0);
+        const double p10 = __shfl_sync(FULL, a[c0], c0 + 1), p11 = __shfl_sync(FULL, a[c0 + 1], c0 + 1);
+        const double p20 = __shfl_sync(FULL, a[c0], c0 + 2), p21 = __shfl_sync(FULL, a[c0 + 1], c0 + 2);
+        const double p22 = __shfl_sync(FULL, a[c0 + 2], c0 + 2);
+        const double p30 = __shfl_sync(FULL, a[c0], c0 + 3), p31 = __shfl_sync(FULL, a[c0 + 1], c0 + 3);
+        const double p32 = __shfl_sync(FULL, a[c0 + 2], c0 + 3), p33 = __shfl_sync(FULL, a[c0 + 3], c0 + 3);
+        double r0, r1, r2, r3, l00, l11, l22, l33;
+        GPP_PIVOT(p00, r0, l00)
+        const double l10 = p10 * r0, l20 = p20 * r0, l30 = p30 * r0;
+        const double d1 = fma(-l10, l10, p11);
+        GPP_PIVOT(d1, r1, l11)
+        const double l21 = fma(-l20, l10, p21) * r1, l31 = fma(-l30, l10, p31) * r1;
+        const double d2 = fma(-l21, l21, fma(-l20, l20, p22));
+        GPP_PIVOT(d2, r2, l22)
+        const double l32 = fma(-l31, l21, fma(-l30, l20, p32)) * r2;
+        const double d3 = fma(-l32, l32, fma(-l31, l31, fma(-l30, l30, p33)));
+        GPP_PIVOT(d3, r3, l33)
+        {
+            int ex;
+            mant *= frexp((l00 * l11) * (l22 * l33), &ex);
+            esum += ex;
+        }
+        // this lane's row against the pivot block
+        double x0 = a[c0] * r0;
+        double x1 = fma(-x0, l10, a[c0 + 1]) * r1;
+        double x2 = fma(-x1, l21, fma(-x0, l20, a[c0 + 2])) * r2;
+        double x3 = fma(-x2, l32, fma(-x1, l31, fma(-x0, l30, a[c0 + 3]))) * r3;
+        const int rel = lane - c0;  // rows of the pivot block: exact diagonal, zeros above it; finished rows: zeros
+        x0 = (rel == 0) ? l00 : ((rel < 0) ? 0.0 : x0);
+        x1 = (rel == 1) ? l11 : ((rel < 1) ? 0.0 : x1);
+        x2 = (rel == 2) ? l22 : ((rel < 2) ? 0.0 : x2);
+        x3 = (rel == 3) ? l33 : ((rel < 3) ? 0.0 : x3);
+        mydinv = (rel == 0) ? r0 : ((rel == 1) ? r1 : ((rel == 2) ? r2 : ((rel == 3) ? r3 : mydinv)));
+        a[c0] = x0;
+        a[c0 + 1] = x1;
+        a[c0 + 2] = x2;
+        a[c0 + 3] = x3;
+        LT[(c0 + 0) * LTLD + lane] = x0;
+        LT[(c0 + 1) * LTLD + lane] = x1;
+        LT[(c0 + 2) * LTLD + lane] = x2;
+        LT[(c0 + 3) * LTLD + lane] = x3;
+        __syncwarp();
+#pragma unroll
+        for (int j = c0 + 4; j < LB; j += 2) {
+            const double2 k0 = *reinterpret_cast<const double2*>(LT + (c0 + 0) * LTLD + j);
+            const double2 k1 = *reinterpret_cast<const double2*>(LT + (c0 + 1) * LTLD + j);
+            const double2 k2 = *reinterpret_cast<const double2*>(LT + (c0 + 2) * LTLD + j);
+            const double2 k3 = *reinterpret_cast<const double2*>(LT + (c0 + 3) * LTLD + j);
+            a[j] = fma(-x3, k3.x, fma(-x2, k2.x, fma(-x1, k1.x, fma(-x0, k0.x, a[j]))));
+            a[j + 1] = fma(-x3, k3.y, fma(-x2, k2.y, fma(-x1, k1.y, fma(-x0, k0.y, a[j + 1]))));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < LB; k += 2) {
+        if (k <= lane) {
+            double2 v;
+            v.x = a[k];
+            v.y = (k + 1 <= lane) ? a[k + 1] : 0.0;
+            *reinterpret_cast<double2*>(row + k) = v;
+        }
+    }
+    xd[b + lane] = mydinv;
+}
+#undef GPP_PIVOT
+
+// rows i0+8w .. i0+8w+7 of the SYRK update of the diagonal sub-block (i0,i0) with block column b (one warp)
+__device__ __forceinline__ void warp_syrk_strip8(double* S, int i0, int b, int w, int g, int t) {
+    double c[4][2];
+#pragma unroll
+    for (int ni = 0; ni < 4; ni++) { c[ni][0] = 0.0; c[ni][1] = 0.0; }
+#pragma unroll
+    for (int kk = 0; kk < LB; kk += 4) {
+        const double af = S[(i0 + 8 * w + g) * LLD + b + kk + t];
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) {
+            if (ni <= w) {
+                const double bf = S[(i0 + ni * 8 + g) * LLD + b + kk + t];
+                dmma884(c[ni][0], c[ni][1], af, bf);
+            }
+        }
+    }
+#pragma unroll
+    for (int ni = 0; ni < 4; ni++) {
+        if (ni <= w) {
+            double2* p2 = reinterpret_cast<double2*>(S + (i0 + 8 * w + g) * LLD + i0 + ni * 8 + 2 * t);
+            double2 v = *p2;
+            v.x -= c[ni][0];
+            v.y -= c[ni][1];
+            *p2 = v;
+        }
+    }
+}
+
 __device__ __forceinline__ void acc_store32(double* dst, int ldd, const double (&acc)[4][4][2], double sgn, int g,
                                             int t) {
 #pragma unroll
@@ -371,6 +491,7 @@ __device__ __forceinline__ void acc_store32(double* dst, int ldd, const double (
 }
 
 // prof (optional): clock64 stamps written by thread 0 / lane 0 of the inverse warp
+template <int GEN>
 __global__ void __launch_bounds__(LEAF_THREADS, 1)
 leaf_potrf_trinv_v2_kernel(double* A, int ld, int kb, double* M, double* logdet_part, int* info, long long* prof) {
     extern __shared__ __align__(16) double sm[];
@@ -410,7 +531,8 @@ leaf_potrf_trinv_v2_kernel(double* A, int ld, int kb, double* M, double* logdet_
         for (int q = 0; q < 4; q++) {
             const int b = q * LB;
             if (warp == 0) {
-                warp_potrf32_v2(S, xd, LT + q * LB * LTLD, b, lane, bad, mant, esum);
+                if (GEN >= 3) warp_potrf32_v3(S, xd, LT + q * LB * LTLD, b, lane, bad, mant, esum);
+                else warp_potrf32_v2(S, xd, LT + q * LB * LTLD, b, lane, bad, mant, esum);
                 __threadfence_block();
                 named_bar_arrive(2 + q, 64);
             }
@@ -420,7 +542,37 @@ leaf_potrf_trinv_v2_kernel(double* A, int ld, int kb, double* M, double* logdet_
             if (warp >= 1 && warp <= 3 - q) warp_trsm_sub32(S, xd, LT + q * LB * LTLD, (q + warp) * LB, b, lane);
             named_bar_sync(1, 224);
             GPP_STAMP(3 + 3 * q)
-            {   // SYRK: A_uw -= L_uq L_wq^T, q < w <= u <= 3; pair 0 = the next diagonal block, owned by warp 0
+            if (GEN >= 3) {
+                // SYRK: the next diagonal block (it gates the next factorisation) in four 8-row strips on warps 0-3,
+                // the other block pairs on warps 4,5,6,1,2 in that order
+                const int i0d = (q + 1) * LB;
+                if (warp < 4) {
+                    warp_syrk_strip8(S, i0d, b, warp, g, t);
+                    named_bar_sync(6, 128);
+                }
+                const int m = 3 - q;
+                const int npairs = m * (m + 1) / 2 - 1;
+                const int slot = (warp >= 4) ? warp - 4 : (warp >= 1 ? warp + 2 : -1);  // warps 4,5,6,1,2,3 -> 0..5
+                if (slot >= 0 && slot < npairs) {
+                    int u = 0, w = slot + 1;  // pair index slot+1 in the (u,w) enumeration, pair 0 is the diagonal
+                    while (w > u) { w -= u + 1; u++; }
+                    const int i0 = (q + 1 + u) * LB, j0 = (q + 1 + w) * LB;
+                    acc_zero(acc);
+                    warp_mm32(acc, [&](int r, int k) { return S[(i0 + r) * LLD + b + k]; },
+                              [&](int k, int c) { return S[(j0 + c) * LLD + b + k]; }, g, t);
+#pragma unroll
+                    for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+                        for (int ni = 0; ni < 4; ni++) {
+                            const int r = mi * 8 + g, c = ni * 8 + 2 * t;
+                            double2* p2 = reinterpret_cast<double2*>(S + (i0 + r) * LLD + j0 + c);
+                            double2 v = *p2;
+                            v.x -= acc[mi][ni][0];
+                            v.y -= acc[mi][ni][1];
+                            *p2 = v;
+                        }
+                }
+            } else {   // SYRK: A_uw -= L_uq L_wq^T, q < w <= u <= 3; pair 0 = the next diagonal block, owned by warp 0
                 const int m = 3 - q;
                 if (warp < m * (m + 1) / 2) {
                     int u = 0, w = warp;
@@ -516,6 +668,7 @@ leaf_potrf_trinv_v2_kernel(double* A, int ld, int kb, double* M, double* logdet_
         }
         double2 x;
         if (bc > bi) {
+            if (GEN >= 3) continue;  // M is zero-initialised once and nothing ever writes above its diagonal blocks
             x.x = 0.0;
             x.y = 0.0;
         } else if (bc == bi) {
@@ -534,18 +687,24 @@ inline cudaError_t chol_set_attributes() {
     cudaError_t e = cudaFuncSetAttribute(leaf_potrf_trinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          LEAF_SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(leaf_potrf_trinv_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF2_SMEM_BYTES);
+    e = cudaFuncSetAttribute(leaf_potrf_trinv_v2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             LEAF2_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(leaf_potrf_trinv_v2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             LEAF2_SMEM_BYTES);
     if (e != cudaSuccess) return e;
     return gemm_set_attributes();
 }
 
-// leaf generation used by the drivers below (2 = leaf_potrf_trinv_v2_kernel)
-inline int g_leaf_version = 2;
+// leaf generation used by the drivers below (1 = first kernel, 2 / 3 = leaf_potrf_trinv_v2_kernel<2 / 3>)
+inline int g_leaf_version = 3;
 
 inline cudaError_t launch_leaf(double* A, int ld, int col, double* M, double* logdet_part, int* info, cudaStream_t st,
                                long long* prof = nullptr) {
-    if (g_leaf_version == 2)
-        leaf_potrf_trinv_v2_kernel<<<1, LEAF_THREADS, LEAF2_SMEM_BYTES, st>>>(A, ld, col, M, logdet_part, info, prof);
+    if (g_leaf_version >= 3)
+        leaf_potrf_trinv_v2_kernel<3><<<1, LEAF_THREADS, LEAF2_SMEM_BYTES, st>>>(A, ld, col, M, logdet_part, info, prof);
+    else if (g_leaf_version == 2)
+        leaf_potrf_trinv_v2_kernel<2><<<1, LEAF_THREADS, LEAF2_SMEM_BYTES, st>>>(A, ld, col, M, logdet_part, info, prof);
     else
         leaf_potrf_trinv_kernel<<<1, LEAF_THREADS, LEAF_SMEM_BYTES, st>>>(A, ld, col, M, logdet_part, info);
     count_launch();
@@ -671,8 +830,8 @@ struct CholLookahead {
 };
 
 // factor tile columns [p0, pend) of the panel on stream st (rows p0..T)
-inline cudaError_t panel_factor(double* A, double* M, int ld, int T, int p0, int pend, double* logdet_part, int* info,
-                                cudaStream_t st) {
+inline cudaError_t panel_factor_base(double* A, double* M, int ld, int T, int p0, int pend, double* logdet_part,
+                                     int* info, cudaStream_t st) {
     for (int col = p0; col < pend; col++) {
         GPP_TRY(launch_leaf(A, ld, col, M, logdet_part, info, st));
         const int below = T - col - 1;
@@ -740,20 +899,37 @@ inline cudaError_t trailing_update(double* A, int ld, int T, int p0, int pend, i
     return launch_gemm(op, true, true, 1, st);
 }
 
+// panels wider than PANEL_BLOCKS are factored recursively: left half, update of the right half with the left
+// (one DMMA GEMM at K = width/2), right half -- so that only PANEL_BLOCKS-wide pieces run at K = 128
+inline cudaError_t panel_factor(double* A, double* M, int ld, int T, int p0, int pend, double* logdet_part, int* info,
+                                cudaStream_t st) {
+    const int w = pend - p0;
+    if (w <= PANEL_BLOCKS) return panel_factor_base(A, M, ld, T, p0, pend, logdet_part, info, st);
+    int half = PANEL_BLOCKS;
+    while (half * 2 < w) half *= 2;
+    const int mid = p0 + half;
+    GPP_TRY(panel_factor(A, M, ld, T, p0, mid, logdet_part, info, st));
+    GPP_TRY(trailing_update(A, ld, T, p0, mid, mid, pend, st));
+    return panel_factor(A, M, ld, T, mid, pend, logdet_part, info, st);
+}
+
 inline cudaError_t potrf_lookahead(double* A, double* M, int ld, int T, double* logdet_part, int* info,
                                    cudaStream_t st, CholLookahead& la) {
-    const int NP = (T + PANEL_BLOCKS - 1) / PANEL_BLOCKS;
+    // K of the trailing update: wide panels only pay off when the trailing matrix is large (measured:
+    // N = 16384 59.0 -> 56.6 ms with 8, N = 8192 12.3 -> 12.8 ms)
+    const int PB = g_panel_blocks > 0 ? g_panel_blocks : (T >= 96 ? 8 : 4);
+    const int NP = (T + PB - 1) / PB;
     if (NP > la.panels) return cudaErrorInvalidValue;
     GPP_TRY(cudaEventRecord(la.fork, st));
     GPP_TRY(cudaStreamWaitEvent(la.side, la.fork, 0));
     int last_tu = -1;  // last panel whose TUr was issued on the main stream
     for (int p = 0; p < NP; p++) {
-        const int p0 = p * PANEL_BLOCKS;
-        const int pend = (p0 + PANEL_BLOCKS < T) ? p0 + PANEL_BLOCKS : T;
+        const int p0 = p * PB;
+        const int pend = (p0 + PB < T) ? p0 + PB : T;
         GPP_TRY(panel_factor(A, M, ld, T, p0, pend, logdet_part, info, la.side));
         GPP_TRY(cudaEventRecord(la.ev_pf[p], la.side));
         if (pend >= T) break;
-        const int nend = (pend + PANEL_BLOCKS < T) ? pend + PANEL_BLOCKS : T;
+        const int nend = (pend + PB < T) ? pend + PB : T;
         if (last_tu >= 0) GPP_TRY(cudaStreamWaitEvent(la.side, la.ev_tu[last_tu], 0));
         GPP_TRY(trailing_update(A, ld, T, p0, pend, pend, nend, la.side));  // TUn(p)
         if (nend < T) {

@@ -5,4 +5,12 @@ likelihoods_noise, priors, optim, bayesian_optimizations, utils, preprocessing, 
 all O(N^2)/O(N^3) arithmetic runs in ``lib/libgpplus_b200.so`` (hand-written sm_100a CUDA, C ABI in
 ``include/gpplus_b200.h``).  There is no CPU fallback.
 """
+import os as _os
+
+# Restart workers keep one CUDA stream per in-flight evaluation.  With the driver's default of 8 hardware
+# work queues, more than 8 streams alias onto the same queue and serialise (measured: engine throughput at
+# N=500 saturates at 5.4k evals/s from 4 threads on; with 32 queues it scales to 19k evals/s at 16 threads).
+# The variable is read when the CUDA context is created, so it must be set before the first CUDA call.
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 __version__ = "0.1.0"

@@ -215,7 +215,7 @@ def _workers_per_gpu(n_train: int) -> int:
         return max(1, int(env))
     # small problems are launch-latency bound: keep several restarts in flight per GPU
     if n_train <= 1024:
-        return 4
+        return 8
     if n_train <= 4096:
         return 2
     return 1

@@ -93,6 +93,109 @@ struct Timer {
     }
 };
 
+
+// ---- instruction latency probes (one warp, dependent chains) ------------------------------------
+__global__ void lat_kernel(double* out, long long* cyc, double seed) {
+    __shared__ double sh[64];
+    const int lane = threadIdx.x;
+    double x = seed + lane * 1e-3, y = 1.0 + seed;
+    long long t0, t1;
+    // dependent DFMA chain
+    t0 = clock64();
+#pragma unroll
+    for (int i = 0; i < 64; i++) x = fma(x, y, 1e-9);
+    t1 = clock64();
+    if (lane == 0) cyc[0] = (t1 - t0) / 64;
+    // dependent rsqrt chain
+    double z = 2.0 + x * 1e-300;
+    t0 = clock64();
+#pragma unroll
+    for (int i = 0; i < 16; i++) z = rsqrt(z) + 1.5;
+    t1 = clock64();
+    if (lane == 0) cyc[1] = (t1 - t0) / 16;
+    // dependent sqrt chain
+    t0 = clock64();
+#pragma unroll
+    for (int i = 0; i < 16; i++) z = sqrt(z) + 1.5;
+    t1 = clock64();
+    if (lane == 0) cyc[2] = (t1 - t0) / 16;
+    // dependent division chain
+    t0 = clock64();
+#pragma unroll
+    for (int i = 0; i < 16; i++) z = 1.0 / z + 1.5;
+    t1 = clock64();
+    if (lane == 0) cyc[3] = (t1 - t0) / 16;
+    // dependent double shuffle chain
+    t0 = clock64();
+#pragma unroll
+    for (int i = 0; i < 32; i++) z = __shfl_sync(0xffffffffu, z, (i * 7) & 31);
+    t1 = clock64();
+    if (lane == 0) cyc[4] = (t1 - t0) / 32;
+    // shared-memory round trip: STS, syncwarp, broadcast LDS
+    t0 = clock64();
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+        sh[lane] = z;
+        __syncwarp();
+        z = sh[(i * 5) & 31] + 1e-12;
+        __syncwarp();
+    }
+    t1 = clock64();
+    if (lane == 0) cyc[5] = (t1 - t0) / 32;
+    // dependent DMMA chain (same accumulator)
+    double c0 = 0.0, c1 = 0.0;
+    t0 = clock64();
+#pragma unroll
+    for (int i = 0; i < 64; i++) dmma884(c0, c1, x, y);
+    t1 = clock64();
+    if (lane == 0) cyc[6] = (t1 - t0) / 64;
+    // independent DMMAs (16 accumulators), issue rate of one warp
+    double a0[16], a1[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) { a0[k] = 0.0; a1[k] = 0.0; }
+    t0 = clock64();
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int k = 0; k < 16; k++) dmma884(a0[k], a1[k], x, y);
+    t1 = clock64();
+    if (lane == 0) cyc[7] = (t1 - t0) / 128;
+    double acc = c0 + c1;
+#pragma unroll
+    for (int k = 0; k < 16; k++) acc += a0[k] + a1[k];
+    // MUFU.RSQ64H-based fast reciprocal sqrt: raw approximation + 2 Newton steps
+    double w = 3.0 + z * 1e-300;
+    t0 = clock64();
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        double r;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(w));
+        double e = fma(-w * r, r, 1.0);
+        r = fma(0.5 * r, e, r);
+        e = fma(-w * r, r, 1.0);
+        r = fma(0.5 * r, e, r);
+        w = r + 2.5;
+    }
+    t1 = clock64();
+    if (lane == 0) cyc[8] = (t1 - t0) / 16;
+    out[lane] = x + z + acc + w;
+}
+
+static void lat_lab(cudaStream_t st) {
+    double* out;
+    long long* cyc;
+    CHECK(cudaMalloc(&out, 32 * 8));
+    CHECK(cudaMalloc(&cyc, 16 * 8));
+    for (int rep = 0; rep < 2; rep++) lat_kernel<<<1, 32, 0, st>>>(out, cyc, 0.5);
+    CHECK(cudaStreamSynchronize(st));
+    long long h[16];
+    CHECK(cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost));
+    printf("latency (cycles): dfma %lld  rsqrt() %lld  sqrt() %lld  div %lld  shfl.f64 %lld  sts+lds roundtrip %lld  dmma dep %lld  "
+           "dmma indep issue %lld  rsqrt.approx+2NR %lld\n", h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8]);
+    cudaFree(out);
+    cudaFree(cyc);
+}
+
 static void leaf_lab(cudaStream_t st) {
     const int ld = 128;
     double *A0, *A, *M, *ldp, *mx;
@@ -111,7 +214,7 @@ static void leaf_lab(cudaStream_t st) {
     Timer tm;
     std::vector<double> Lref(128 * 128), Mref(128 * 128), Lh(128 * 128), Mh(128 * 128);
     double ldref = 0;
-    for (int ver = 1; ver <= 2; ver++) {
+    for (int ver = 1; ver <= 3; ver++) {
         g_leaf_version = ver;
         float best = 1e9f, sum = 0;
         for (int it = 0; it < 12; it++) {
@@ -119,7 +222,7 @@ static void leaf_lab(cudaStream_t st) {
             CHECK(cudaMemsetAsync(M, 0, 128 * 128 * 8, st));
             CHECK(cudaMemsetAsync(prof, 0, 16 * 8, st));
             tm.start(st);
-            CHECK(launch_leaf(A, ld, 0, M, ldp, info, st, ver == 2 ? prof : nullptr));
+            CHECK(launch_leaf(A, ld, 0, M, ldp, info, st, ver >= 2 ? prof : nullptr));
             float ms = tm.stop(st);
             if (it >= 2) { best = fminf(best, ms); sum += ms; }
         }
@@ -146,7 +249,7 @@ static void leaf_lab(cudaStream_t st) {
             double du = 0;
             for (int i = 0; i < 128; i++)
                 for (int j = i + 1; j < 128; j++) du = fmax(du, fabs(Mh[i * 128 + j]));
-            printf("   v2 vs v1: |dL|max %.3e |dM|max %.3e |M upper|max %.3e dlogdet %.3e\n", dl, dm, du, hld - ldref);
+            printf("   vs v1: |dL|max %.3e |dM|max %.3e |M upper|max %.3e dlogdet %.3e\n", dl, dm, du, hld - ldref);
             long long hp[16];
             CHECK(cudaMemcpy(hp, prof, sizeof(hp), cudaMemcpyDeviceToHost));
             const char* names[16] = {"start", "loaded", "potrf0", "trsm0", "syrk0", "potrf1", "trsm1", "syrk1", "potrf2",
@@ -231,14 +334,15 @@ static void potrf_lab(int n, cudaStream_t st) {
     CholLookahead la;
     CHECK(la.init(T));
     Timer tm;
-    struct Var { const char* name; int leaf, bm, look; };
-    const Var vars[] = {{"blocked  leaf1 bm128", 1, 128, 0}, {"blocked  leaf2 bm128", 2, 128, 0},
-                        {"lookahead leaf2 bm128", 2, 128, 1}, {"lookahead leaf2 bm64 ", 2, 64, 1},
-                        {"blocked  leaf2 bm64 ", 2, 64, 0}};
+    struct Var { const char* name; int leaf, bm, look, pb; };
+    const Var vars[] = {{"blocked  leaf2 bm64 P4 ", 2, 64, 0, 4}, {"lookahead leaf2 bm64 P4 ", 2, 64, 1, 4},
+                        {"lookahead leaf3 bm64 P4 ", 3, 64, 1, 4}, {"lookahead leaf2 bm64 P8 ", 2, 64, 1, 8},
+                        {"lookahead leaf3 bm64 P8 ", 3, 64, 1, 8}};
     const int nblk = (int)((ld * ld + 255) / 256);
     for (int v = 0; v < 5; v++) {
         g_leaf_version = vars[v].leaf;
         g_gemm_bm = vars[v].bm;
+        g_panel_blocks = vars[v].pb;
         float best = 1e9f;
         for (int it = 0; it < 3; it++) {
             CHECK(cudaMemcpyAsync(A, A0, (size_t)ld * ld * 8, cudaMemcpyDeviceToDevice, st));
@@ -272,7 +376,8 @@ static void potrf_lab(int n, cudaStream_t st) {
         fflush(stdout);
     }
     g_leaf_version = 2;
-    g_gemm_bm = 128;
+    g_gemm_bm = 64;
+    g_panel_blocks = 4;
     la.destroy();
     cudaFree(A0); cudaFree(A); cudaFree(M); cudaFree(Lref); cudaFree(ldp); cudaFree(mx); cudaFree(info);
 }
@@ -282,8 +387,9 @@ int main(int argc, char** argv) {
     CHECK(chol_set_attributes());
     cudaStream_t st;
     CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    lat_lab(st);
     leaf_lab(st);
-    gemm_lab(st);
+    if (getenv("LAB_GEMM")) gemm_lab(st);
     std::vector<int> ns;
     for (int i = 1; i < argc; i++) ns.push_back(atoi(argv[i]));
     if (ns.empty()) ns = {2048, 8192, 16384};
