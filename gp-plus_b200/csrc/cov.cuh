@@ -18,7 +18,8 @@
 namespace gpp {
 
 constexpr int CT = 128;          // tile edge (points)
-constexpr int COV_THREADS = 256;
+constexpr int COV_THREADS = 512;  // 16 warps, 4 x 4 grid of 32x32 warp tiles: 64 accumulator registers per thread
+                                  // (the 8-warp / 32x64 layout ran at 12 % warp occupancy and was latency-bound)
 constexpr int ZP = 4;            // latent-coordinate stride per point (GPP_MAX_DZ)
 
 enum { KERNEL_EXPSQ = 0, KERNEL_MATERN32 = 1, KERNEL_MATERN52 = 2 };
@@ -132,7 +133,7 @@ struct CovArgs {
 };
 
 inline size_t cov_smem_bytes(int dqp) {
-    return 128 + sizeof(double) * (size_t)(2 * CT * dqp + 2 * CT + 2 * CT * ZP + CT + 2 * CT);
+    return 128 + sizeof(double) * (size_t)(2 * CT * dqp + 2 * CT + 2 * CT * ZP + CT + 4 * CT);
 }
 
 __device__ __forceinline__ void tri_decode(int bid, int& ti, int& tj) {
@@ -143,28 +144,28 @@ __device__ __forceinline__ void tri_decode(int bid, int& ti, int& tj) {
     tj = bid - (int)((long long)t * (t + 1) / 2);
 }
 
-// cross term acc[mi][ni][e] = xs_i . xs_j on DMMA; warp (4 x 2 grid) owns rows wm0..+32, cols wn0..+64
+// cross term acc[mi][ni][e] = xs_i . xs_j on DMMA; warp (4 x 4 grid) owns rows wm0..+32, cols wn0..+32
 __device__ __forceinline__ void tile_cross_dmma(const double* Xi, const double* Xj, int dqp, int wm0, int wn0, int g,
-                                                int t, double (&acc)[4][8][2]) {
+                                                int t, double (&acc)[4][4][2]) {
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
-        for (int j = 0; j < 8; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+        for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
     for (int kk = 0; kk < dqp; kk += 4) {
-        double af[4], bf[8];
+        double af[4], bf[4];
 #pragma unroll
         for (int mi = 0; mi < 4; mi++) af[mi] = Xi[(wm0 + mi * 8 + g) * dqp + kk + t];
 #pragma unroll
-        for (int ni = 0; ni < 8; ni++) bf[ni] = Xj[(wn0 + ni * 8 + g) * dqp + kk + t];
+        for (int ni = 0; ni < 4; ni++) bf[ni] = Xj[(wn0 + ni * 8 + g) * dqp + kk + t];
 #pragma unroll
         for (int mi = 0; mi < 4; mi++)
 #pragma unroll
-            for (int ni = 0; ni < 8; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+            for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
     }
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(COV_THREADS) cov_tile_kernel(const CovArgs a) {
+__global__ void __launch_bounds__(COV_THREADS, 1) cov_tile_kernel(const CovArgs a) {
     extern __shared__ __align__(128) unsigned char smraw[];
     const int dqp = a.dqp, dz = a.dz;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smraw);
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(COV_THREADS) cov_tile_kernel(const CovArgs a) 
     double* zi = snj + CT;
     double* zj = zi + CT * ZP;
     double* sal = zj + CT * ZP;  // alpha of the column points
-    double* red = sal + CT;      // [2][CT]
+    double* red = sal + CT;      // [4][CT]
 
     const int tid = threadIdx.x;
     int ti, tj;
@@ -208,8 +209,8 @@ __global__ void __launch_bounds__(COV_THREADS) cov_tile_kernel(const CovArgs a) 
 
     const int warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int wm0 = (warp >> 1) * 32, wn0 = (warp & 1) * 64;
-    double acc[4][8][2];
+    const int wm0 = (warp >> 2) * 32, wn0 = (warp & 3) * 32;
+    double acc[4][4][2];
     tile_cross_dmma(Xi, Xj, dqp, wm0, wn0, g, t, acc);
 
     const bool diag_tile = a.same && (ti == tj);
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(COV_THREADS) cov_tile_kernel(const CovArgs a) 
         for (int k = 0; k < ZP; k++) zr[k] = (k < dz) ? zi[row * ZP + k] : 0.0;
         double msum = 0.0;
 #pragma unroll
-        for (int ni = 0; ni < 8; ni++) {
+        for (int ni = 0; ni < 4; ni++) {
             double kv[2];
 #pragma unroll
             for (int e = 0; e < 2; e++) {
@@ -265,12 +266,14 @@ __global__ void __launch_bounds__(COV_THREADS) cov_tile_kernel(const CovArgs a) 
         if (a.alpha) {
             msum += __shfl_xor_sync(0xffffffffu, msum, 1);
             msum += __shfl_xor_sync(0xffffffffu, msum, 2);
-            if (t == 0) red[(warp & 1) * CT + row] = msum;
+            if (t == 0) red[(warp & 3) * CT + row] = msum;
         }
     }
     if (a.alpha) {
         __syncthreads();
-        if (tid < CT) a.mean_part[(long long)tj * a.ld_part + (long long)ti * CT + tid] = red[tid] + red[CT + tid];
+        if (tid < CT)
+            a.mean_part[(long long)tj * a.ld_part + (long long)ti * CT + tid] =
+                (red[tid] + red[CT + tid]) + (red[2 * CT + tid] + red[3 * CT + tid]);
     }
 }
 
@@ -289,15 +292,15 @@ struct GradArgs {
 };
 
 inline size_t grad_smem_bytes(int dqp) {
-    // bar | Xi Xj | ni nj | zi zj | ai aj | rowacc[2][CT][ZP] | colacc[4][CT][ZP] | wred[8][1+dqp]
-    return 128 + sizeof(double) * (size_t)(2 * CT * dqp + 2 * CT + 2 * CT * ZP + 2 * CT + 2 * CT * ZP + 4 * CT * ZP +
-                                           8 * (1 + dqp));
+    // bar | Xi Xj | ni nj | zi zj | ai aj | rowacc[4][CT][ZP] | colacc[4][CT][ZP] | wred[16][1+dqp]
+    return 128 + sizeof(double) * (size_t)(2 * CT * dqp + 2 * CT + 2 * CT * ZP + 2 * CT + 4 * CT * ZP + 4 * CT * ZP +
+                                           16 * (1 + dqp));
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(COV_THREADS) grad_tile_kernel(const GradArgs a) {
+template <int KIND, bool HAS_Z>
+__global__ void __launch_bounds__(COV_THREADS, 1) grad_tile_kernel(const GradArgs a) {
     extern __shared__ __align__(128) unsigned char smraw[];
-    const int dqp = a.dqp, dz = a.dz;
+    const int dqp = a.dqp, dz = HAS_Z ? a.dz : 0;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smraw);
     double* Xi = reinterpret_cast<double*>(smraw + 128);
     double* Xj = Xi + CT * dqp;
@@ -307,9 +310,9 @@ __global__ void __launch_bounds__(COV_THREADS) grad_tile_kernel(const GradArgs a
     double* zj = zi + CT * ZP;
     double* sai = zj + CT * ZP;
     double* saj = sai + CT;
-    double* rowacc = saj + CT;            // [2][CT][ZP]
-    double* colacc = rowacc + 2 * CT * ZP;  // [4][CT][ZP]
-    double* wred = colacc + 4 * CT * ZP;    // [8][1+dqp]
+    double* rowacc = saj + CT;              // [4][CT][ZP]
+    double* colacc = rowacc + 4 * CT * ZP;  // [4][CT][ZP]
+    double* wred = colacc + 4 * CT * ZP;    // [16][1+dqp]
 
     const int tid = threadIdx.x;
     int ti, tj;
@@ -338,8 +341,8 @@ __global__ void __launch_bounds__(COV_THREADS) grad_tile_kernel(const GradArgs a
 
     const int warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int wm0 = (warp >> 1) * 32, wn0 = (warp & 1) * 64;
-    double acc[4][8][2];
+    const int wm0 = (warp >> 2) * 32, wn0 = (warp & 3) * 32;
+    double acc[4][4][2];
     tile_cross_dmma(Xi, Xj, dqp, wm0, wn0, g, t, acc);
 
     const bool diag_tile = (ti == tj);
@@ -354,7 +357,7 @@ __global__ void __launch_bounds__(COV_THREADS) grad_tile_kernel(const GradArgs a
         for (int k = 0; k < ZP; k++) rowz[mi][k] = 0.0;
 
 #pragma unroll
-    for (int ni = 0; ni < 8; ni++) {
+    for (int ni = 0; ni < 4; ni++) {
         double colz[2][ZP];
 #pragma unroll
         for (int e = 0; e < 2; e++)
@@ -417,7 +420,7 @@ __global__ void __launch_bounds__(COV_THREADS) grad_tile_kernel(const GradArgs a
                         v += __shfl_xor_sync(0xffffffffu, v, 4);
                         v += __shfl_xor_sync(0xffffffffu, v, 8);
                         v += __shfl_xor_sync(0xffffffffu, v, 16);
-                        if (g == 0) colacc[((warp >> 1) * CT + wn0 + ni * 8 + 2 * t + e) * ZP + k] = v;
+                        if (g == 0) colacc[((warp >> 2) * CT + wn0 + ni * 8 + 2 * t + e) * ZP + k] = v;
                     }
                 }
         }
@@ -431,7 +434,7 @@ __global__ void __launch_bounds__(COV_THREADS) grad_tile_kernel(const GradArgs a
                     double v = rowz[mi][k];
                     v += __shfl_xor_sync(0xffffffffu, v, 1);
                     v += __shfl_xor_sync(0xffffffffu, v, 2);
-                    if (t == 0) rowacc[((warp & 1) * CT + wm0 + mi * 8 + g) * ZP + k] = v;
+                    if (t == 0) rowacc[((warp & 3) * CT + wm0 + mi * 8 + g) * ZP + k] = v;
                 }
             }
     }
@@ -449,7 +452,7 @@ __global__ void __launch_bounds__(COV_THREADS) grad_tile_kernel(const GradArgs a
         for (int mi = 0; mi < 4; mi++) xi_d[mi] = Xi[(wm0 + mi * 8 + g) * dqp + d];
         double sd = 0.0;
 #pragma unroll
-        for (int ni = 0; ni < 8; ni++)
+        for (int ni = 0; ni < 4; ni++)
 #pragma unroll
             for (int e = 0; e < 2; e++) {
                 const double xj = Xj[(wn0 + ni * 8 + 2 * t + e) * dqp + d];
@@ -467,13 +470,14 @@ __global__ void __launch_bounds__(COV_THREADS) grad_tile_kernel(const GradArgs a
     if (tid < 1 + a.dq) {
         double v = 0.0;
 #pragma unroll
-        for (int w = 0; w < 8; w++) v += wred[w * (1 + dqp) + tid];
+        for (int w = 0; w < 16; w++) v += wred[w * (1 + dqp) + tid];
         a.tile_part[(long long)blockIdx.x * (1 + dqp) + tid] = v;
     }
     if (dz > 0 && tid < CT) {
         // slot (tj, point of block ti): row partials; slot (ti, point of block tj): column partials
         for (int k = 0; k < dz; k++) {
-            double v = rowacc[(0 * CT + tid) * ZP + k] + rowacc[(1 * CT + tid) * ZP + k];
+            double v = (rowacc[(0 * CT + tid) * ZP + k] + rowacc[(1 * CT + tid) * ZP + k]) +
+                       (rowacc[(2 * CT + tid) * ZP + k] + rowacc[(3 * CT + tid) * ZP + k]);
             a.zpart[((long long)tj * a.np + (long long)ti * CT + tid) * ZP + k] = v;
             if (!diag_tile) {
                 double c = colacc[(0 * CT + tid) * ZP + k] + colacc[(1 * CT + tid) * ZP + k] +
@@ -584,9 +588,12 @@ inline cudaError_t cov_set_attributes() {
     GPP_SET(cov_tile_kernel<KERNEL_EXPSQ>)
     GPP_SET(cov_tile_kernel<KERNEL_MATERN32>)
     GPP_SET(cov_tile_kernel<KERNEL_MATERN52>)
-    GPP_SET(grad_tile_kernel<KERNEL_EXPSQ>)
-    GPP_SET(grad_tile_kernel<KERNEL_MATERN32>)
-    GPP_SET(grad_tile_kernel<KERNEL_MATERN52>)
+    GPP_SET((grad_tile_kernel<KERNEL_EXPSQ, true>))
+    GPP_SET((grad_tile_kernel<KERNEL_MATERN32, true>))
+    GPP_SET((grad_tile_kernel<KERNEL_MATERN52, true>))
+    GPP_SET((grad_tile_kernel<KERNEL_EXPSQ, false>))
+    GPP_SET((grad_tile_kernel<KERNEL_MATERN32, false>))
+    GPP_SET((grad_tile_kernel<KERNEL_MATERN52, false>))
 #undef GPP_SET
     return cudaSuccess;
 }
@@ -606,9 +613,15 @@ inline cudaError_t launch_grad(const GradArgs& a, int kind, cudaStream_t st) {
     int nt = a.T * (a.T + 1) / 2;
     size_t sm = grad_smem_bytes(a.dqp);
     count_launch();
-    if (kind == KERNEL_EXPSQ) grad_tile_kernel<KERNEL_EXPSQ><<<nt, COV_THREADS, sm, st>>>(a);
-    else if (kind == KERNEL_MATERN32) grad_tile_kernel<KERNEL_MATERN32><<<nt, COV_THREADS, sm, st>>>(a);
-    else grad_tile_kernel<KERNEL_MATERN52><<<nt, COV_THREADS, sm, st>>>(a);
+    if (a.dz > 0) {
+        if (kind == KERNEL_EXPSQ) grad_tile_kernel<KERNEL_EXPSQ, true><<<nt, COV_THREADS, sm, st>>>(a);
+        else if (kind == KERNEL_MATERN32) grad_tile_kernel<KERNEL_MATERN32, true><<<nt, COV_THREADS, sm, st>>>(a);
+        else grad_tile_kernel<KERNEL_MATERN52, true><<<nt, COV_THREADS, sm, st>>>(a);
+    } else {
+        if (kind == KERNEL_EXPSQ) grad_tile_kernel<KERNEL_EXPSQ, false><<<nt, COV_THREADS, sm, st>>>(a);
+        else if (kind == KERNEL_MATERN32) grad_tile_kernel<KERNEL_MATERN32, false><<<nt, COV_THREADS, sm, st>>>(a);
+        else grad_tile_kernel<KERNEL_MATERN52, false><<<nt, COV_THREADS, sm, st>>>(a);
+    }
     return cudaGetLastError();
 }
 

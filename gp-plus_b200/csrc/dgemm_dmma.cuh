@@ -131,19 +131,38 @@ __global__ void __launch_bounds__(GemmCfg<BM>::THREADS, GemmCfg<BM>::MIN_CTAS) d
     const int tile_id = (SPLIT == 1) ? (int)blockIdx.x : (int)(blockIdx.x / SPLIT);
     const int r0 = half * BM;  // first row of this CTA inside its 128-row tile
 
+    // Tile rasterisation: super-rows of GS tile rows, column-major inside a super-row, so that the ~150 tiles in
+    // flight share GS row panels and ~150/GS column panels instead of one row panel and ~150 column panels
+    // (LAUUM at N=16384 read 21 GB from DRAM for 3.2 GB of algorithmic traffic with the plain row-major order).
+    constexpr int GS = 8;
     int ti, tj;
     if (op.map == MAP_TRI) {
-        // bid -> (ti,tj), tj <= ti, ti ascending (tiles with the longest K range first for LAUUM)
-        int bid = tile_id;
-        int t = (int)((sqrt(8.0 * (double)bid + 1.0) - 1.0) * 0.5);
-        while ((long long)(t + 1) * (t + 2) / 2 <= bid) t++;
-        while ((long long)t * (t + 1) / 2 > bid) t--;
-        ti = t;
-        tj = bid - (int)((long long)t * (t + 1) / 2);
+        // lower tiles (tj <= ti); super-row gq holds rows [GS*gq, GS*gq + R), tiles before it: r0g (r0g + 1) / 2
+        const int bid = tile_id;
+        int gq = (int)((sqrt(8.0 * (double)bid + 1.0) - 1.0) * 0.5) / GS;
+        while ((long long)(gq + 1) * GS * ((gq + 1) * GS + 1) / 2 <= bid) gq++;
+        while ((long long)gq * GS * (gq * GS + 1) / 2 > bid) gq--;
+        const int r0g = gq * GS;
+        const int R = (op.tiles_m - r0g < GS) ? (op.tiles_m - r0g) : GS;
+        int local = bid - (int)((long long)r0g * (r0g + 1) / 2);
+        const int rect = r0g * R;  // full columns 0 .. r0g-1, R tiles each
+        if (local < rect) {
+            tj = local / R;
+            ti = r0g + (local - tj * R);
+        } else {
+            local -= rect;
+            int c = 0;  // triangular corner: column r0g + c holds rows r0g + c .. r0g + R - 1
+            while (local >= R - c) { local -= R - c; c++; }
+            tj = r0g + c;
+            ti = r0g + c + local;
+        }
         if (ti >= tm) return;
     } else {
-        ti = tile_id / op.tiles_n;
-        tj = tile_id - ti * op.tiles_n;
+        const int r0g = (tile_id / (GS * op.tiles_n)) * GS;
+        const int R = (op.tiles_m - r0g < GS) ? (op.tiles_m - r0g) : GS;
+        const int local = tile_id - r0g * op.tiles_n;
+        tj = local / R;
+        ti = r0g + (local - tj * R);
         if (ti >= tm) return;
         if (op.lower_filter && (ti + op.lower_off < tj)) return;
     }
