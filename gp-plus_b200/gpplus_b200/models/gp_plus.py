@@ -423,6 +423,114 @@ class GP_Plus(GPR):
                              "function, which is a preprocessing function.")
         return zeta[index, :]
 
+    # ------------------------------------------------------------------------------------------
+    # consumers of the batched prediction kernel
+    def Sobol(self, N=10000):
+        """First-order and total Sobol sensitivity indices of the fitted emulator (models/gp_plus.py:1148-1224):
+        Saltelli's A / B / AB_i design, (p + 2) * N predictions, all served by the batched predict kernel.
+
+        Returns ``(S, ST)`` of shape [1, p].  Differences from the reference source, which cannot run as
+        written: its ``normalize_sobol_sequence`` returns from inside the loop over categorical columns (only the
+        first one is rounded, and a model without categorical inputs gets ``None``); here every categorical column
+        is mapped to its levels.  The low-discrepancy points come from ``scipy.stats.qmc.Sobol(scramble=False)``
+        (first point skipped, like ``sobol_seq.i4_sobol_generate``), since ``sobol_seq`` is not a dependency."""
+        from scipy.stats.qmc import Sobol as _Sobol
+        if N < 1e5:
+            warnings.warn("Increase N for accuracy!")
+        x = self.train_inputs[0].detach().double().cpu()
+        p = x.shape[1]
+        seq = torch.from_numpy(_Sobol(d=2 * p, scramble=False).random(N + 1)[1:])
+        mins, maxs = x.min(dim=0)[0], x.max(dim=0)[0]
+        parts = []
+        for unit in (seq[:, p:], seq[:, :p]):
+            pts = mins + (maxs - mins) * unit
+            for k, col in enumerate(self._qual_cols):
+                pts[:, col] = (unit[:, col] * (self.num_levels_per_var[k] - 1)).round()
+            parts.append(pts)
+        A, B = parts
+        FA = self.predict(A, return_std=False).detach().cpu().numpy().reshape(-1, 1)
+        FB = self.predict(B, return_std=False).detach().cpu().numpy().reshape(-1, 1)
+        S, ST = np.zeros((p, 1)), np.zeros((p, 1))
+        for i in range(p):
+            ABi = A.clone()
+            ABi[:, i] = B[:, i]
+            Fi = self.predict(ABi, return_std=False).detach().cpu().numpy().reshape(-1, 1)
+            S[i, :] = np.sum(FB * (Fi - FA), axis=0) / N
+            ST[i, :] = np.sum((FA - Fi) ** 2, axis=0) / (2 * N)
+        varY = np.var(np.concatenate([FA, FB]), axis=0)
+        return (S / varY).T, (ST / varY).T
+
+    def evaluation(self, Xtest, ytest, return_metrics: bool = False):
+        """Test-set metrics of models/gp_plus.py:889-932: joint negative log predictive density per point (the
+        full-covariance predictive of gpytorch.metrics.negative_log_predictive_density), MSE, MAE, RRMSE and the
+        95 % interval score, in the original y units.
+
+        The joint NLPD never forms the M x M predictive covariance: by the Schur-complement identity
+        ``log p(y* | y) = log p(y, y*) - log p(y)`` it is the difference of two marginal-likelihood evaluations
+        on the engine (training set alone, and training + test set with the test points' own noise groups)."""
+        from tabulate import tabulate
+        Xtest = data_type_check(Xtest).detach().double().cpu()
+        ytest = data_type_check(ytest).detach().double().cpu().reshape(-1)
+        self.eval()
+        y_sc = (ytest - self.y_min) / self.y_std
+        with torch.no_grad():
+            mean, std = self.predict(Xtest, return_std=True, include_noise=True)
+        mu = (mean - self.y_min) / self.y_std
+        sd = std / self.y_std
+        xtr = self.train_inputs[0].detach().double().cpu()
+        if self._level_strides is not None and self.relevel_on_predict:
+            # the joint evaluation must see the test categories exactly as predict() does (eval-mode re-ranking)
+            saved = self.relevel_on_predict
+            lv_te = self._level_index(Xtest, False)
+            self.relevel_on_predict = False
+            try:
+                lv_tr = self._level_index(xtr, True)
+            finally:
+                self.relevel_on_predict = saved
+            joint_levels = np.concatenate([lv_tr, lv_te])
+        else:
+            joint_levels = None
+        nll_train = self._joint_nll_with_levels(xtr, self.train_targets, None, True)
+        nll_joint = self._joint_nll_with_levels(torch.cat([xtr, Xtest]), torch.cat([self.train_targets.double(), y_sc]),
+                                                joint_levels, False)
+        m = ytest.shape[0]
+        nlpd = (nll_joint - nll_train) / m
+        mse = torch.mean((mu - y_sc) ** 2) * self.y_std ** 2
+        mae = torch.mean(torch.abs(mu - y_sc)) * torch.abs(self.y_std)
+        lo, up = mu - 2.0 * sd, mu + 2.0 * sd  # MultivariateNormal.confidence_region: mean -/+ 2 std
+        score = (up - lo) + (y_sc > up) * 2 / 0.05 * (y_sc - up) + (y_sc < lo) * 2 / 0.05 * (lo - y_sc)
+        iscore = score.mean() * torch.abs(self.y_std)
+        rrmse = torch.sqrt(mse / torch.var(ytest))
+        table_data = [["Negative Log-Likelihood (NLL)", nlpd], ["Mean Squared Error (MSE)", mse],
+                      ["Mean Absolute Error  (MAE)", mae], ["Relative Root Mean Square Error (RRMSE)", rrmse],
+                      ["Interval Score (IS)", iscore]]
+        print(tabulate(table_data, headers=["Metric", "Value"], tablefmt="fancy_grid", colalign=("left", "left")))
+        if return_metrics:
+            return {"NLL": float(nlpd), "MSE": float(mse), "MAE": float(mae), "RRMSE": float(rrmse),
+                    "IS": float(iscore)}
+
+    def _joint_nll_with_levels(self, x, y_scaled, levels, training: bool) -> float:
+        from .. import _engine
+        from .gpregression import get_default_device
+        xc = x.detach().double().cpu()
+        cols = self._quant_columns()
+        qk = self._quant_kernel() if len(cols) > 0 else None
+        table = self._latent_table()
+        n_mean, _ = self._mean_layout()
+        if levels is None:
+            levels = self._level_index(xc, training)
+        eng = _engine.Engine(
+            xq=xc[:, cols].numpy() if qk is not None else None, y=y_scaled.detach().double().cpu().numpy(),
+            kernel=qk.family if qk is not None else _engine.KERNEL_EXPSQ, level_idx=levels,
+            n_combo=0 if table is None else int(table.shape[0]), dz=0 if table is None else int(table.shape[1]),
+            noise_idx=self._noise_index(xc), n_noise=int(self.likelihood.noise_covar.raw_noise.numel()),
+            mean_idx=self._mean_index(xc), n_mean=n_mean, device=get_default_device())
+        try:
+            return float(eng.mll_grad(self._hyper_numpy(), want_grad=False)["nll"])
+        finally:
+            eng.close()
+
+
     def get_latent_space(self):
         if len(self.qual_kernel_columns) == 0:
             raise RuntimeError("No categorical Variable, No latent positions")

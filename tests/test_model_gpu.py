@@ -1,5 +1,7 @@
 """The drop-in Python API on the GPU: MLLObjective.fun, fit_model_scipy and predict of GP_Plus against the
 model-level CPU oracle, on the reference's example workloads (BASELINE.json configs 1-3)."""
+import math
+
 import numpy as np
 import pytest
 import torch
@@ -194,3 +196,70 @@ def test_native_objective_equals_torch_path(maker):
         assert abs(f - f_ref) <= 1e-10 * max(1.0, abs(f_ref))
         assert np.max(np.abs(g - g_ref)) <= 1e-9 * max(1.0, np.max(np.abs(g_ref)))
         assert isinstance(obj.fun_fast(th, False), float)
+
+
+def test_evaluation_joint_nlpd_matches_dense_oracle():
+    """GP_Plus.evaluation (gp_plus.py:889-932): joint NLPD via the two-likelihood identity against the dense
+    full-covariance predictive computed on the CPU; MSE / MAE / RRMSE / IS against their definitions."""
+    from oracle import gp_oracle as O
+    m, spec, Xte, yte = _c3()
+    torch.manual_seed(5)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+        m.likelihood.noise_covar.raw_noise.fill_(-4.0)
+    Xte, yte = Xte[:40], yte[:40]
+    got = m.evaluation(Xte, yte, return_metrics=True)
+    # dense reference
+    h = m._hyper_numpy()
+    xtr = m.train_inputs[0].double()
+    cols = m._quant_columns()
+    w, z, sf2 = torch.tensor(h["w"]), torch.tensor(h["z"]), h["sigma_f2"]
+    noise, beta = torch.tensor(h["noise"]), torch.tensor(h["beta"])
+    ltr = torch.as_tensor(m._level_index(xtr, True), dtype=torch.long)
+    lte = torch.as_tensor(m._level_index(Xte, False), dtype=torch.long)
+    kind = m._quant_kernel().family
+    centre = xtr[:, cols].mean(0, keepdim=True)
+    Ktt = O.covariance(xtr[:, cols], ltr, xtr[:, cols], ltr, w, z, sf2, kind, centre=centre)
+    Kst = O.covariance(Xte[:, cols], lte, xtr[:, cols], ltr, w, z, sf2, kind, centre=centre)
+    Kss = O.covariance(Xte[:, cols], lte, Xte[:, cols], lte, w, z, sf2, kind, centre=centre)
+    ntr = noise[torch.as_tensor(m._noise_index(xtr), dtype=torch.long)]
+    nte = noise[torch.as_tensor(m._noise_index(Xte), dtype=torch.long)]
+    mtr = O._mean_vector(torch.as_tensor(m._mean_index(xtr), dtype=torch.long), beta, len(beta))
+    mte = O._mean_vector(torch.as_tensor(m._mean_index(Xte), dtype=torch.long), beta, len(beta))
+    L = torch.linalg.cholesky(Ktt + torch.diag(ntr))
+    alpha = torch.cholesky_solve((m.train_targets.double() - mtr).unsqueeze(-1), L).squeeze(-1)
+    mu = mte + Kst @ alpha
+    V = torch.linalg.solve_triangular(L, Kst.T, upper=False)
+    Sig = Kss - V.T @ V + torch.diag(nte)
+    y_sc = (yte.double() - m.y_min) / m.y_std
+    dist = torch.distributions.MultivariateNormal(mu, covariance_matrix=Sig)
+    nlpd = float(-dist.log_prob(y_sc) / y_sc.shape[0])
+    assert abs(got["NLL"] - nlpd) <= 1e-7 * max(1.0, abs(nlpd))
+    sd = torch.sqrt(torch.diagonal(Sig))
+    mse = float(torch.mean((mu - y_sc) ** 2) * m.y_std ** 2)
+    assert abs(got["MSE"] - mse) <= 1e-8 * mse
+    assert abs(got["RRMSE"] - math.sqrt(mse / float(torch.var(yte.double())))) <= 1e-8
+    lo, up = mu - 2 * sd, mu + 2 * sd
+    isc = ((up - lo) + (y_sc > up) * 40.0 * (y_sc - up) + (y_sc < lo) * 40.0 * (lo - y_sc)).mean() * abs(float(m.y_std))
+    assert abs(got["IS"] - float(isc)) <= 1e-7 * float(isc)
+
+
+def test_sobol_indices_of_an_additive_function():
+    """GP_Plus.Sobol (gp_plus.py:1148-1224) on y = 2 x0 + x1^2 + level effect: first-order and total indices
+    coincide (no interactions) and sum to one."""
+    from gpplus_b200.models import GP_Plus
+    from gpplus_b200.optim import fit_model_scipy
+    rng = np.random.default_rng(0)
+    n = 240
+    X = np.hstack([rng.uniform(-1, 1, (n, 3)), rng.integers(0, 3, (n, 1)).astype(float)])
+    y = 2.0 * X[:, 0] + X[:, 1] ** 2 + 0.5 * X[:, 3]
+    m = GP_Plus(torch.tensor(X), torch.tensor(y), qual_dict={3: 3}, dtype=torch.float64)
+    torch.manual_seed(0)
+    fit_model_scipy(m, num_restarts=4, bounds=True)
+    with pytest.warns(UserWarning):
+        S, ST = m.Sobol(N=4096)
+    assert S.shape == (1, 4) and ST.shape == (1, 4)
+    assert abs(S.sum() - 1.0) < 0.05 and np.all(np.abs(S - ST) < 0.05)
+    assert abs(S[0, 2]) < 0.02            # x2 is inert
+    assert S[0, 0] > S[0, 1] > 0.0        # var(2 x0) = 4/3 > var(x1^2) = 4/45
