@@ -30,26 +30,17 @@ from .AFs import AF_HF, AF_LF
 _KIND = {"HF": _engine.ACQ_HF, "LF": _engine.ACQ_LF, "EI": _engine.ACQ_EI}
 
 
-def acquisition_table_argmax(model, table_x, best_values: Sequence[float], cost_by_source: Sequence[float],
-                             maximize: bool = True, si: float = 0.0, kinds: Optional[Sequence[str]] = None,
-                             return_scores: bool = False):
-    """Arg-max of the cost-scaled acquisition over a candidate table (BO_GP_plus.py:183-194).
-
-    ``table_x`` [M, d] holds model inputs whose LAST column is the source index.  Candidates are scored in
-    source-major order -- all rows of source 0 (AF_HF_Engineering), then source 1, ... (AF_LF_Engineering) --
-    exactly the order of ``torch.cat(scores)`` in the reference, with ``include_noise=False``.  Returns
-    ``(best_score, index_in_source_major_order, order)`` where ``order`` maps that position back to a row of
-    ``table_x``; with ``return_scores`` the source-major score vector of THIS rank's chunk is appended.
-    """
+def prepare_candidate_table(model, table_x, n_src: int) -> Dict:
+    """Host-side preparation of THIS rank's chunk of a candidate table: source-major order, quantitative columns,
+    level / mean / cost indices.  The result can be scored repeatedly (``score_prepared``), from host arrays or --
+    after ``to_device`` -- from arrays already resident on the engine's GPU."""
     x = np.asarray(table_x, dtype=np.float64)
-    n_src = len(best_values)
     src = np.rint(x[:, -1]).astype(np.int64)
     # stable source-major order without a comparison sort: the positions of every source, concatenated
     per_src = [np.flatnonzero(src == s) for s in range(n_src)]
     order = np.concatenate(per_src) if n_src > 0 else np.zeros(0, dtype=np.int64)
     bounds = np.concatenate([[0], np.cumsum([len(v) for v in per_src])])
     m = int(order.shape[0])
-    kinds = list(kinds) if kinds is not None else ["HF"] + ["LF"] * (n_src - 1)
     eng = model._ensure_factor()
     cols = model._quant_columns()
     has_lvl = eng.dz > 0
@@ -83,19 +74,57 @@ def acquisition_table_argmax(model, table_x, best_values: Sequence[float], cost_
             if mean_idx is None:
                 mean_idx = np.zeros(mc, dtype=np.int32)
             mean_idx[a - lo:b - lo] = mi
+    return {"xq": xq, "cost_idx": cost_idx, "level_idx": lvl, "mean_idx": mean_idx, "order": order, "lo": lo,
+            "count": mc}
 
-    if mc > 0:
+
+def to_device(prep: Dict, device: int) -> Dict:
+    """Copy the per-candidate arrays of a prepared chunk to GPU ``device`` (contiguous torch tensors)."""
+    out = dict(prep)
+    dev = torch.device("cuda", device)
+    for key in ("xq", "cost_idx", "level_idx", "mean_idx"):
+        if prep[key] is not None:
+            out[key] = torch.from_numpy(np.ascontiguousarray(prep[key])).to(dev).contiguous()
+    return out
+
+
+def score_prepared(model, prep: Dict, best_values: Sequence[float], cost_by_source: Sequence[float],
+                   maximize: bool = True, si: float = 0.0, kinds: Optional[Sequence[str]] = None,
+                   return_scores: bool = False):
+    """Fused predict + acquisition + arg-max over a prepared chunk, then the arg-max over ranks."""
+    n_src = len(best_values)
+    kinds = list(kinds) if kinds is not None else ["HF"] + ["LF"] * (n_src - 1)
+    eng = model._ensure_factor()
+    if prep["count"] > 0:
         res = eng.acq_argmax(
-            xq, cost_idx, cost=list(cost_by_source), kind_by_cost=[_KIND[k] for k in kinds],
-            best_f=list(best_values), level_idx=lvl, mean_idx=mean_idx, maximize=maximize, si=si,
-            y_min=float(model.y_min), y_std=float(model.y_std), return_scores=return_scores)
-        score, idx = res[0], int(res[1]) + lo
+            prep["xq"], prep["cost_idx"], cost=list(cost_by_source), kind_by_cost=[_KIND[k] for k in kinds],
+            best_f=list(best_values), level_idx=prep["level_idx"], mean_idx=prep["mean_idx"], maximize=maximize,
+            si=si, y_min=float(model.y_min), y_std=float(model.y_std), return_scores=return_scores)
+        score, idx = res[0], int(res[1]) + prep["lo"]
     else:
         res, score, idx = (None, None, np.zeros(0)), -np.inf, -1
     score, idx = parallel.global_argmax(score, idx)
     if return_scores:
-        return score, idx, order, res[2]
-    return score, idx, order
+        return score, idx, res[2]
+    return score, idx
+
+
+def acquisition_table_argmax(model, table_x, best_values: Sequence[float], cost_by_source: Sequence[float],
+                             maximize: bool = True, si: float = 0.0, kinds: Optional[Sequence[str]] = None,
+                             return_scores: bool = False):
+    """Arg-max of the cost-scaled acquisition over a candidate table (BO_GP_plus.py:183-194).
+
+    ``table_x`` [M, d] holds model inputs whose LAST column is the source index.  Candidates are scored in
+    source-major order -- all rows of source 0 (AF_HF_Engineering), then source 1, ... (AF_LF_Engineering) --
+    exactly the order of ``torch.cat(scores)`` in the reference, with ``include_noise=False``.  Returns
+    ``(best_score, index_in_source_major_order, order)`` where ``order`` maps that position back to a row of
+    ``table_x``; with ``return_scores`` the source-major score vector of THIS rank's chunk is appended.
+    """
+    prep = prepare_candidate_table(model, table_x, len(best_values))
+    out = score_prepared(model, prep, best_values, cost_by_source, maximize, si, kinds, return_scores)
+    if return_scores:
+        return out[0], out[1], prep["order"], out[2]
+    return out[0], out[1], prep["order"]
 
 
 def _slice_labels(model, x: np.ndarray, rows: np.ndarray):
