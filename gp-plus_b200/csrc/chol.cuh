@@ -477,6 +477,33 @@ __device__ __forceinline__ void warp_syrk_strip8(double* S, int i0, int b, int w
     }
 }
 
+
+// One warp: X = L_bb^-1 by right-looking substitution on the identity (lane c owns column c): the dependent
+// chain per row is one multiply and one FMA instead of a half-row dot product.  LT[j][i] = L_ij.
+__device__ __forceinline__ void warp_trinv32_v3(const double* LT, const double* xd, double* Xd, int b, int lane) {
+    double x[LB];
+#pragma unroll
+    for (int r = 0; r < LB; r++) x[r] = (r == lane) ? 1.0 : 0.0;
+#pragma unroll
+    for (int r = 0; r < LB; r++) {
+        x[r] *= xd[b + r];
+        const double xr = x[r];
+#pragma unroll
+        for (int k = (r + 1) & ~1; k < LB; k += 2) {
+            const double2 lk = *reinterpret_cast<const double2*>(LT + r * LTLD + k);
+            if (k > r) x[k] = fma(-xr, lk.x, x[k]);
+            x[k + 1] = fma(-xr, lk.y, x[k + 1]);
+        }
+        Xd[r * TLD + lane] = xr;
+    }
+}
+
+// One warp: copy rows [r0, r1) x 32 columns of a shared-memory block (leading dimension lds) to global memory
+__device__ __forceinline__ void warp_store_rows32(const double* src, int lds, double* dst, long long ldg, int r0,
+                                                  int r1, int lane) {
+    for (int r = r0; r < r1; r++) dst[(long long)r * ldg + lane] = src[r * lds + lane];
+}
+
 __device__ __forceinline__ void acc_store32(double* dst, int ldd, const double (&acc)[4][4][2], double sgn, int g,
                                             int t) {
 #pragma unroll
@@ -522,7 +549,14 @@ leaf_potrf_trinv_v2_kernel(double* A, int ld, int kb, double* M, double* logdet_
         // inverse warp: X_qq as soon as L_qq is final
         for (int q = 0; q < 4; q++) {
             named_bar_sync(2 + q, 64);
-            warp_trinv32_v2(S, xd, Xd + q * LB * TLD, q * LB, lane);
+            if (GEN >= 4) {
+                warp_trinv32_v3(LT + q * LB * LTLD, xd, Xd + q * LB * TLD, q * LB, lane);
+                __syncwarp();
+                // the diagonal sub-block of the inverse is final: store it now, off the tail
+                warp_store_rows32(Xd + q * LB * TLD, TLD, Mb + (long long)(q * LB) * ld + q * LB, ld, 0, LB, lane);
+            } else {
+                warp_trinv32_v2(S, xd, Xd + q * LB * TLD, q * LB, lane);
+            }
         }
         if (prof && lane == 0) prof[15] = clock64();
     } else {
@@ -549,6 +583,14 @@ leaf_potrf_trinv_v2_kernel(double* A, int ld, int kb, double* M, double* logdet_
                 if (warp < 4) {
                     warp_syrk_strip8(S, i0d, b, warp, g, t);
                     named_bar_sync(6, 128);
+                }
+                if (GEN >= 4 && warp == 3) {
+                    // block column q of L is final (diagonal sub-block after the factorisation, the rows below it
+                    // after the substitution): stream it out while the other warps update the trailing blocks
+                    for (int r = b; r < TILE; r++) {
+                        const int c = b + lane;
+                        if (c <= r) Ab[(long long)r * ld + c] = S[r * LLD + c];
+                    }
                 }
                 const int m = 3 - q;
                 const int npairs = m * (m + 1) / 2 - 1;
@@ -657,6 +699,20 @@ leaf_potrf_trinv_v2_kernel(double* A, int ld, int kb, double* M, double* logdet_
     GPP_STAMP(12)
 #undef GPP_T
 
+    if (GEN >= 4) {
+        // everything except the last diagonal sub-block of L and the six off-diagonal sub-blocks of the inverse
+        // has already been stored; 7 block copies over 8 warps
+        if (warp == 7) {
+            for (int r = 3 * LB; r < TILE; r++) {
+                const int c = 3 * LB + lane;
+                if (c <= r) Ab[(long long)r * ld + c] = S[r * LLD + c];
+            }
+        } else if (warp < 6) {
+            int i = 1, j = warp;
+            while (j >= i) { j -= i; i++; }  // warp -> (i,j): (1,0) (2,0) (2,1) (3,0) (3,1) (3,2)
+            warp_store_rows32(GPP_XOFF(i, j), LLD, Mb + (long long)(i * LB) * ld + j * LB, ld, 0, LB, lane);
+        }
+    } else {
     // write back: L (lower) to A_kk, X (lower, zeros above) to M_kk; 16-byte coalesced stores
     for (int idx = tid; idx < TILE * (TILE / 2); idx += LEAF_THREADS) {
         const int i = idx >> 6, c = (idx & 63) * 2;
@@ -678,6 +734,7 @@ leaf_potrf_trinv_v2_kernel(double* A, int ld, int kb, double* M, double* logdet_
         }
         *reinterpret_cast<double2*>(Mb + (long long)i * ld + c) = x;
     }
+    }
 #undef GPP_XOFF
     GPP_STAMP(13)
 #undef GPP_STAMP
@@ -693,15 +750,20 @@ inline cudaError_t chol_set_attributes() {
     e = cudaFuncSetAttribute(leaf_potrf_trinv_v2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              LEAF2_SMEM_BYTES);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(leaf_potrf_trinv_v2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             LEAF2_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
     return gemm_set_attributes();
 }
 
 // leaf generation used by the drivers below (1 = first kernel, 2 / 3 = leaf_potrf_trinv_v2_kernel<2 / 3>)
-inline int g_leaf_version = 3;
+inline int g_leaf_version = 4;
 
 inline cudaError_t launch_leaf(double* A, int ld, int col, double* M, double* logdet_part, int* info, cudaStream_t st,
                                long long* prof = nullptr) {
-    if (g_leaf_version >= 3)
+    if (g_leaf_version >= 4)
+        leaf_potrf_trinv_v2_kernel<4><<<1, LEAF_THREADS, LEAF2_SMEM_BYTES, st>>>(A, ld, col, M, logdet_part, info, prof);
+    else if (g_leaf_version == 3)
         leaf_potrf_trinv_v2_kernel<3><<<1, LEAF_THREADS, LEAF2_SMEM_BYTES, st>>>(A, ld, col, M, logdet_part, info, prof);
     else if (g_leaf_version == 2)
         leaf_potrf_trinv_v2_kernel<2><<<1, LEAF_THREADS, LEAF2_SMEM_BYTES, st>>>(A, ld, col, M, logdet_part, info, prof);

@@ -214,7 +214,7 @@ static void leaf_lab(cudaStream_t st) {
     Timer tm;
     std::vector<double> Lref(128 * 128), Mref(128 * 128), Lh(128 * 128), Mh(128 * 128);
     double ldref = 0;
-    for (int ver = 1; ver <= 3; ver++) {
+    for (int ver = 1; ver <= 4; ver++) {
         g_leaf_version = ver;
         float best = 1e9f, sum = 0;
         for (int it = 0; it < 12; it++) {
@@ -336,8 +336,8 @@ static void potrf_lab(int n, cudaStream_t st) {
     Timer tm;
     struct Var { const char* name; int leaf, bm, look, pb; };
     const Var vars[] = {{"blocked  leaf2 bm64 P4 ", 2, 64, 0, 4}, {"lookahead leaf2 bm64 P4 ", 2, 64, 1, 4},
-                        {"lookahead leaf3 bm64 P4 ", 3, 64, 1, 4}, {"lookahead leaf2 bm64 P8 ", 2, 64, 1, 8},
-                        {"lookahead leaf3 bm64 P8 ", 3, 64, 1, 8}};
+                        {"lookahead leaf3 bm64 P4 ", 3, 64, 1, 4}, {"lookahead leaf4 bm64 P4 ", 4, 64, 1, 4},
+                        {"lookahead leaf4 bm64 P8 ", 4, 64, 1, 8}};
     const int nblk = (int)((ld * ld + 255) / 256);
     for (int v = 0; v < 5; v++) {
         g_leaf_version = vars[v].leaf;
