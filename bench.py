@@ -366,16 +366,27 @@ def run_fit(args):
         return run_fit_reference(args)
     world, rank, local = _dist_setup()
     set_default_device(local)
-    Xtr, ytr, Xte, yte, qd = _c2_problem()
-    model = GP_Plus(Xtr, ytr, qual_dict=qd, dtype=torch.float64)
+    options = {"maxiter": args.maxiter} if args.maxiter > 0 else {}
+    if args.fit_config == "c4":
+        X, y = make_workload(args.n)
+        Xtr, ytr = torch.from_numpy(X[: args.n - 256]), torch.from_numpy(y[: args.n - 256])
+        Xte, yte = torch.from_numpy(X[args.n - 256:]), torch.from_numpy(y[args.n - 256:])
+        model = GP_Plus(Xtr, ytr, dtype=torch.float64, quant_correlation_class="Matern52Kernel")
+        what = "synthetic wing N=%d D=10 Matern-5/2, %d restarts (+1), L-BFGS-B%s" % (
+            Xtr.shape[0], args.restarts, " maxiter=%d" % args.maxiter if args.maxiter > 0 else " reference defaults")
+    else:
+        Xtr, ytr, Xte, yte, qd = _c2_problem()
+        model = GP_Plus(Xtr, ytr, qual_dict=qd, dtype=torch.float64)
+        what = "borehole mixed-variable, n=%d, 2 categorical x 5 levels, rough-RBF x latent map, %d restarts (+1), " \
+               "L-BFGS-B reference defaults" % (Xtr.shape[0], args.restarts)
     torch.manual_seed(0)
     obj = MLLObjective(model, True, [0, 0])
     theta0 = [_sample_from_prior(model) for _ in range(args.restarts + 1)]
-    fit_model_scipy(model, num_restarts=0, theta0_list=theta0[:2])  # warm-up: library load, first launches
+    fit_model_scipy(model, num_restarts=0, theta0_list=theta0[:world], options={"maxiter": 1})  # warm-up
     torch.cuda.synchronize()
     l0 = E.launch_count()
     t0 = time.time()
-    res, best = fit_model_scipy(model, add_prior=True, num_restarts=args.restarts, theta0_list=theta0)
+    res, best = fit_model_scipy(model, add_prior=True, num_restarts=args.restarts, theta0_list=theta0, options=options)
     torch.cuda.synchronize()
     dt = time.time() - t0
     if rank == 0:
@@ -386,8 +397,7 @@ def run_fit(args):
         print(json.dumps({
             "metric": "64-restart fit time", "value": dt, "unit": "s", "n_gpus": world, "higher_is_better": False,
             "scaling": "strong", "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "borehole mixed-variable, n=%d, 2 categorical x 5 levels, rough-RBF x latent map, "
-                                   "%d restarts (+1), L-BFGS-B reference defaults" % (Xtr.shape[0], args.restarts)},
+            "config": {"workload": what},
             "objective_evals": nfev, "evals_per_s": nfev / dt, "failed_starts": failed, "best_neg_log_posterior": best,
             "test_rrmse": rrmse, "gpu_launches": E.launch_count() - l0}), flush=True)
     if world > 1:
@@ -531,6 +541,9 @@ def main():
                     help="mll (default, the headline metric) | fit: 64-restart fit of BASELINE configs[1] | "
                          "acq: predictive mean/var + acquisition arg-max over --candidates (configs[4])")
     ap.add_argument("--restarts", type=int, default=64)
+    ap.add_argument("--maxiter", type=int, default=0, help="fit workload: cap on L-BFGS-B iterations (0 = reference default)")
+    ap.add_argument("--fit-config", default="c2", choices=["c2", "c4"],
+                    help="fit workload: c2 = borehole mixed n=500 (configs[1]); c4 = synthetic N=--n D=10 Matern-5/2 (configs[3])")
     ap.add_argument("--candidates", type=int, default=1000000)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours" and args.workload == "mll":

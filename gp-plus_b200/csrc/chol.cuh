@@ -28,6 +28,7 @@ constexpr int LLD = 132;   // smem leading dimension: 132 = 4 (mod 16) keeps eve
 constexpr int TLD = 36;    // per-warp scratch leading dimension (same residue)
 constexpr int LEAF_SMEM_BYTES = (TILE * LLD + TILE + 3 * LB * TLD) * 8;
 constexpr int PANEL_BLOCKS = 4;   // leaf-level panel: in-panel updates run at K = 128
+inline int g_panel_base = 2;       // widest piece factored with K = 128 in-panel updates (recursion stops here)
 inline int g_panel_blocks = 0;     // look-ahead panel width in 128-columns; 0 = by size (8 from N = 12288, else 4)
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -966,14 +967,16 @@ inline cudaError_t trailing_update(double* A, int ld, int T, int p0, int pend, i
 inline cudaError_t panel_factor(double* A, double* M, int ld, int T, int p0, int pend, double* logdet_part, int* info,
                                 cudaStream_t st) {
     const int w = pend - p0;
-    if (w <= PANEL_BLOCKS) return panel_factor_base(A, M, ld, T, p0, pend, logdet_part, info, st);
-    int half = PANEL_BLOCKS;
+    if (w <= g_panel_base) return panel_factor_base(A, M, ld, T, p0, pend, logdet_part, info, st);
+    int half = g_panel_base;
     while (half * 2 < w) half *= 2;
     const int mid = p0 + half;
     GPP_TRY(panel_factor(A, M, ld, T, p0, mid, logdet_part, info, st));
     GPP_TRY(trailing_update(A, ld, T, p0, mid, mid, pend, st));
     return panel_factor(A, M, ld, T, mid, pend, logdet_part, info, st);
 }
+
+inline int g_lookahead_depth = 2;  // 1: the next panel waits for the whole previous trailing update; 2: see below
 
 inline cudaError_t potrf_lookahead(double* A, double* M, int ld, int T, double* logdet_part, int* info,
                                    cudaStream_t st, CholLookahead& la) {
@@ -982,9 +985,15 @@ inline cudaError_t potrf_lookahead(double* A, double* M, int ld, int T, double* 
     const int PB = g_panel_blocks > 0 ? g_panel_blocks : (T >= 96 ? 8 : 4);
     const int NP = (T + PB - 1) / PB;
     if (NP > la.panels) return cudaErrorInvalidValue;
+    const bool deep = g_lookahead_depth >= 2;
     GPP_TRY(cudaEventRecord(la.fork, st));
     GPP_TRY(cudaStreamWaitEvent(la.side, la.fork, 0));
-    int last_tu = -1;  // last panel whose TUr was issued on the main stream
+    // Depth-2 schedule.  U(p,c) = update of panel c's tile columns with panel p.
+    //   side:  PF(0) U(0,1) PF(1) [wait U(0,2)] U(1,2) PF(2) [wait U(1,3)] U(2,3) ...
+    //   main:  [wait PF(0)] U(0,2) U(0,3..) [wait PF(1)] U(1,3) U(1,4..) ...
+    // The side chain only waits for U(p-1,p+1), which the main stream issues BEFORE the bulk U(p-1,p+2..), so it can
+    // run one panel further ahead than with a single trailing launch per panel (depth 1).
+    int last_ev = -1;  // last panel with a recorded ev_tu (U(p,p+2) at depth 2, the whole trailing update at depth 1)
     for (int p = 0; p < NP; p++) {
         const int p0 = p * PB;
         const int pend = (p0 + PB < T) ? p0 + PB : T;
@@ -992,13 +1001,20 @@ inline cudaError_t potrf_lookahead(double* A, double* M, int ld, int T, double* 
         GPP_TRY(cudaEventRecord(la.ev_pf[p], la.side));
         if (pend >= T) break;
         const int nend = (pend + PB < T) ? pend + PB : T;
-        if (last_tu >= 0) GPP_TRY(cudaStreamWaitEvent(la.side, la.ev_tu[last_tu], 0));
-        GPP_TRY(trailing_update(A, ld, T, p0, pend, pend, nend, la.side));  // TUn(p)
+        if (last_ev >= 0) GPP_TRY(cudaStreamWaitEvent(la.side, la.ev_tu[last_ev], 0));
+        GPP_TRY(trailing_update(A, ld, T, p0, pend, pend, nend, la.side));  // U(p,p+1)
         if (nend < T) {
             GPP_TRY(cudaStreamWaitEvent(st, la.ev_pf[p], 0));
-            GPP_TRY(trailing_update(A, ld, T, p0, pend, nend, T, st));       // TUr(p)
-            GPP_TRY(cudaEventRecord(la.ev_tu[p], st));
-            last_tu = p;
+            if (deep) {
+                const int n2end = (nend + PB < T) ? nend + PB : T;
+                GPP_TRY(trailing_update(A, ld, T, p0, pend, nend, n2end, st));  // U(p,p+2)
+                GPP_TRY(cudaEventRecord(la.ev_tu[p], st));
+                GPP_TRY(trailing_update(A, ld, T, p0, pend, n2end, T, st));     // U(p,p+3..)
+            } else {
+                GPP_TRY(trailing_update(A, ld, T, p0, pend, nend, T, st));
+                GPP_TRY(cudaEventRecord(la.ev_tu[p], st));
+            }
+            last_ev = p;
         }
     }
     GPP_TRY(cudaEventRecord(la.join, la.side));

@@ -259,3 +259,58 @@ def test_acquisition_functions_match_the_oracle_formulas():
         ref = -O.acquisition(np.array([0.4]), np.array([0.2]), kind, 0.1, np.array([10.0]), maximize=False)
         assert np.allclose(np.asarray(val).reshape(-1), ref, rtol=1e-13)
         assert np.allclose(stub.seen.numpy(), [[1.0, 1.0, 1.0, 2.0]])
+
+
+@pytest.mark.parametrize("kwargs", [
+    dict(), dict(quant_correlation_class="Matern52Kernel"), dict(quant_correlation_class="RBFKernel"),
+    dict(qual=True), dict(qual=True, multiple_noise=True, m_gp="multiple_constant"), dict(qual=True, fix_noise=True),
+    dict(m_gp="single_zero"),
+])
+def test_closed_form_host_objective_equals_torch_path(kwargs):
+    """optim/_fast_objective.py (the layout gpp_objective evaluates natively) against MLLObjective.fun's torch
+    path -- float32 cast, transforms, every prior family, chain rule -- through a stub engine, on prior draws."""
+    from gpplus_b200.models import GP_Plus
+    from gpplus_b200.optim import _fast_objective as FO
+    from gpplus_b200.optim.mll_scipy import MLLObjective, _sample_from_prior
+    rng = np.random.default_rng(2)
+    n = 40
+    kw = dict(kwargs)
+    qual = kw.pop("qual", False)
+    X = np.hstack([rng.standard_normal((n, 3)), rng.integers(0, 3, (n, 1)).astype(float)])
+    y = np.sin(X[:, 0]) + 0.3 * X[:, 3] + 0.05 * rng.standard_normal(n)
+    if qual:
+        kw["qual_dict"] = {3: 3}
+    m = GP_Plus(torch.tensor(X), torch.tensor(y), dtype=torch.float64, **kw)
+    obj = MLLObjective(m, True, [0, 0])
+    fast = FO.build(m, True, [0, 0])
+    assert fast is not None
+    assert FO.self_check(obj, fast, trials=3, tol=1e-12)
+    spec = fast.layout_spec()
+    assert spec["p"] == obj.pack_parameters().shape[0]
+    table = m._latent_table()
+    n_mean, _ = m._mean_layout()
+    stub = FO._StubEngine(len(m._quant_columns()), 0 if table is None else int(table.shape[1]),
+                          0 if table is None else int(table.shape[0]),
+                          int(m.likelihood.noise_covar.raw_noise.numel()), n_mean)
+    m.__dict__["_get_engine"] = lambda: stub
+    torch.manual_seed(3)
+    for k in range(20):
+        th = _sample_from_prior(m) * (1.0 if k < 15 else 2.5)
+        f_ref, g_ref = obj.fun(th)
+        f, g = fast.fun(th, stub.mll_grad)
+        if np.isfinite(f_ref):
+            assert abs(f - f_ref) <= 1e-12 * max(1.0, abs(f_ref))
+            assert np.max(np.abs(g - g_ref)) <= 1e-11 * max(1.0, np.max(np.abs(g_ref)))
+
+
+def test_host_objective_falls_back_for_unsupported_models():
+    from gpplus_b200.models import GP_Plus
+    from gpplus_b200.optim import _fast_objective as FO
+    rng = np.random.default_rng(0)
+    X = np.hstack([rng.standard_normal((30, 2)), rng.integers(0, 3, (30, 1)).astype(float)])
+    y = X[:, 0] + 0.1 * X[:, 2]
+    m = GP_Plus(torch.tensor(X), torch.tensor(y), qual_dict={2: 3}, dtype=torch.float64, NN_layers_embedding=[4])
+    assert FO.build(m, True, [0, 0]) is None            # tanh MLP latent map: torch path only
+    m2 = GP_Plus(torch.tensor(X), torch.tensor(y), qual_dict={2: 3}, dtype=torch.float64)
+    assert FO.build(m2, True, [0.1, 0]) is None         # weight regularisation: torch path only
+    assert FO.build(m2, False, [0, 0]) is not None

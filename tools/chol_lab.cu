@@ -334,15 +334,17 @@ static void potrf_lab(int n, cudaStream_t st) {
     CholLookahead la;
     CHECK(la.init(T));
     Timer tm;
-    struct Var { const char* name; int leaf, bm, look, pb; };
-    const Var vars[] = {{"blocked  leaf2 bm64 P4 ", 2, 64, 0, 4}, {"lookahead leaf2 bm64 P4 ", 2, 64, 1, 4},
-                        {"lookahead leaf3 bm64 P4 ", 3, 64, 1, 4}, {"lookahead leaf4 bm64 P4 ", 4, 64, 1, 4},
-                        {"lookahead leaf4 bm64 P8 ", 4, 64, 1, 8}};
+    struct Var { const char* name; int leaf, bm, look, pb, depth, base; };
+    const Var vars[] = {{"blocked  leaf4 P4          ", 4, 64, 0, 4, 1, 4}, {"look d1 leaf4 P8 base4    ", 4, 64, 1, 8, 1, 4},
+                        {"look d1 leaf4 P8 base2    ", 4, 64, 1, 8, 1, 2}, {"look d2 leaf4 P8 base2    ", 4, 64, 1, 8, 2, 2},
+                        {"look d2 leaf4 P4 base2    ", 4, 64, 1, 4, 2, 2}};
     const int nblk = (int)((ld * ld + 255) / 256);
     for (int v = 0; v < 5; v++) {
         g_leaf_version = vars[v].leaf;
         g_gemm_bm = vars[v].bm;
         g_panel_blocks = vars[v].pb;
+        g_lookahead_depth = vars[v].depth;
+        g_panel_base = vars[v].base;
         float best = 1e9f;
         for (int it = 0; it < 3; it++) {
             CHECK(cudaMemcpyAsync(A, A0, (size_t)ld * ld * 8, cudaMemcpyDeviceToDevice, st));
@@ -377,7 +379,9 @@ static void potrf_lab(int n, cudaStream_t st) {
     }
     g_leaf_version = 2;
     g_gemm_bm = 64;
-    g_panel_blocks = 4;
+    g_panel_blocks = 0;
+    g_lookahead_depth = 2;
+    g_panel_base = 2;
     la.destroy();
     cudaFree(A0); cudaFree(A); cudaFree(M); cudaFree(Lref); cudaFree(ldp); cudaFree(mx); cudaFree(info);
 }
