@@ -536,7 +536,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=N_HEADLINE)
+    ap.add_argument("--n", "--size", dest="n", type=int, default=N_HEADLINE,
+                    help="training-set size (use --size under torchrun: its own parser claims the prefix --n)")
     ap.add_argument("--workload", default="mll", choices=["mll", "fit", "acq"],
                     help="mll (default, the headline metric) | fit: 64-restart fit of BASELINE configs[1] | "
                          "acq: predictive mean/var + acquisition arg-max over --candidates (configs[4])")

@@ -23,8 +23,11 @@ and the published gpytorch semantics summarised in SURVEY.md Appendix A (covar_d
 expansion with mean-centring, clamp at 0, MaternKernel / RBFKernel formulas, psd_safe_cholesky
 jitter ladder, exact prediction with variance clamped at min_variance).
 
-It is pinned only against closed forms derivable by hand from that code (tests/test_oracle.py:
-N=1 and N=2 likelihoods, kernel limits, finite differences).
+It is pinned against closed forms derivable by hand from that code (tests/test_oracle.py: N=1 and N=2
+likelihoods, kernel limits, finite differences) and, as an independent implementation of the same exact-GP
+mathematics, against scikit-learn's GaussianProcessRegressor (log marginal likelihood, its gradient and the
+predictive mean / variance for the RBF, Matern-3/2 and Matern-5/2 families).  Neither is the reference
+itself, hence "unpinned".
 
 Everything here works on the *natural* parameterisation that crosses the C ABI
 (include/gpplus_b200.h): distance weights w, latent table Z, outputscale, noise variances, mean

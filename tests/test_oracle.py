@@ -203,3 +203,41 @@ def test_golden_fixtures_reproduce():
         r = O.mll(p, h, mode="direct")
         assert r["nll"] == pytest.approx(float(g["r_nll"]), rel=1e-11), f
         assert np.allclose(r["d_w"], g["r_d_w"], rtol=1e-7, atol=1e-9), f
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_oracle_against_scikit_learn_gpr(kind):
+    """Independent pin: scikit-learn's GaussianProcessRegressor evaluates the same exact-GP log marginal likelihood
+    (Cholesky based, Rasmussen & Williams alg. 2.1) and its gradient for ConstantKernel * {RBF, Matern} + WhiteKernel.
+    Mapping: k = sf2 * f(sum_d w_d dx_d^2);  RBF: l_d = 1/sqrt(2 w_d);  Matern: l_d = 1/sqrt(w_d)."""
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    from sklearn.gaussian_process.kernels import RBF, ConstantKernel, Matern, WhiteKernel
+    rng = np.random.default_rng(11)
+    n, dq = 70, 4
+    X = rng.standard_normal((n, dq))
+    y = np.sin(X[:, 0]) + 0.4 * X[:, 1] ** 2 + 0.1 * rng.standard_normal(n)
+    w = np.array([0.3, 1.1, 0.05, 0.6])
+    sf2, noise = 0.8, 0.02
+    p = {"n": n, "dq": dq, "dz": 0, "n_combo": 0, "n_noise": 1, "n_mean": 0, "kernel": kind, "xq": X, "y": y,
+         "level_idx": None, "noise_idx": None, "mean_idx": None}
+    h = {"w": w, "z": None, "sigma_f2": sf2, "noise": np.array([noise]), "beta": None}
+    ref = O.mll(p, h, want_grad=True)
+    if kind == 0:
+        ls = 1.0 / np.sqrt(2.0 * w)
+        base = RBF(length_scale=ls)
+    else:
+        ls = 1.0 / np.sqrt(w)
+        base = Matern(length_scale=ls, nu=1.5 if kind == 1 else 2.5)
+    kernel = ConstantKernel(sf2) * base + WhiteKernel(noise)
+    gpr = GaussianProcessRegressor(kernel=kernel, optimizer=None, alpha=0.0, normalize_y=False).fit(X, y)
+    lml, grad = gpr.log_marginal_likelihood(gpr.kernel_.theta, eval_gradient=True)
+    assert abs(-lml - ref["nll"]) <= 1e-9 * abs(ref["nll"])
+    # sklearn's theta = log(sf2), log(l_1..l_d), log(noise); d nll/d log sf2 = sf2 * d_sf2; d/d log l_d = -2 w_d d_w
+    g_ref = np.concatenate([[sf2 * ref["d_sigma_f2"]], -2.0 * w * ref["d_w"], [noise * ref["d_noise"][0]]])
+    assert np.max(np.abs(-grad - g_ref)) <= 1e-7 * max(1.0, np.max(np.abs(g_ref)))
+    # predictions
+    Xs = rng.standard_normal((9, dq))
+    mu, sd = gpr.predict(Xs, return_std=True)
+    mu_o, var_o = O.predict(p, h, {"m": 9, "xq": Xs, "level_idx": None}, include_noise=True)
+    assert np.max(np.abs(mu - mu_o)) <= 1e-8
+    assert np.max(np.abs(sd ** 2 - var_o)) <= 1e-8
