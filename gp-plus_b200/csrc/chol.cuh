@@ -860,7 +860,9 @@ inline cudaError_t potrf_blocked(double* A, double* M, int ld, int T, double* lo
 // TUr(p) = update of everything to the right of the next panel (lower tiles, the O(N^3) part).
 struct CholLookahead {
     cudaStream_t side = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr;
+    cudaStream_t inv = nullptr;   // lowest priority: early part of the triangular inverse, fills idle SMs
+    cudaEvent_t fork = nullptr, join = nullptr, inv_done = nullptr;
+    bool inv_pending = false;
     std::vector<cudaEvent_t> ev_pf, ev_tu;
     int panels = 0;
 
@@ -868,8 +870,10 @@ struct CholLookahead {
         int lo = 0, hi = 0;
         GPP_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         GPP_TRY(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, hi));
+        GPP_TRY(cudaStreamCreateWithPriority(&inv, cudaStreamNonBlocking, lo));
         GPP_TRY(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
         GPP_TRY(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
+        GPP_TRY(cudaEventCreateWithFlags(&inv_done, cudaEventDisableTiming));
         panels = (T + PANEL_BLOCKS - 1) / PANEL_BLOCKS;
         ev_pf.resize(panels);
         ev_tu.resize(panels);
@@ -886,9 +890,11 @@ struct CholLookahead {
         ev_tu.clear();
         if (fork) cudaEventDestroy(fork);
         if (join) cudaEventDestroy(join);
+        if (inv_done) cudaEventDestroy(inv_done);
         if (side) cudaStreamDestroy(side);
-        fork = join = nullptr;
-        side = nullptr;
+        if (inv) cudaStreamDestroy(inv);
+        fork = join = inv_done = nullptr;
+        side = inv = nullptr;
     }
 };
 
@@ -937,9 +943,11 @@ inline cudaError_t panel_factor_base(double* A, double* M, int ld, int T, int p0
 }
 
 // C[i,j] -= sum_{k in [p0,pend)} A[i,k] A[j,k]^T for tile rows i >= r0, tile columns j in [c0, c1), i >= j
-inline cudaError_t trailing_update(double* A, int ld, int T, int p0, int pend, int c0, int c1, cudaStream_t st) {
+inline cudaError_t trailing_update(double* A, int ld, int T, int p0, int pend, int c0, int c1, cudaStream_t st,
+                                   int max_ctas = 0) {
     if (c1 <= c0 || c0 >= T) return cudaSuccess;
     GemmOp op = gemm_default();
+    op.max_ctas = max_ctas;
     op.A = A + (long long)c0 * TILE * ld + (long long)p0 * TILE;
     op.lda = ld;
     op.B = op.A;
@@ -978,14 +986,25 @@ inline cudaError_t panel_factor(double* A, double* M, int ld, int T, int p0, int
 
 inline int g_lookahead_depth = 2;  // 1: the next panel waits for the whole previous trailing update; 2: see below
 
+inline int g_tu_max_ctas = 0;       // cap on the CTAs of the bulk trailing update (0 = none): leaves SMs to the panel chain
+inline int g_inv_max_ctas = 0;      // cap on the CTAs of the overlapped inverse GEMMs
+inline int g_overlap_inverse = 1;   // start the early part of L^-1 (trtri_early) as soon as its columns of L are final
+
+// defined below; X is the scratch of the triangular inverse (may be null: no overlap)
+inline cudaError_t trtri_early(const double* L, double* M, double* X, int ld, int T, cudaStream_t st);
+inline int trtri_split_point(int T);
+
 inline cudaError_t potrf_lookahead(double* A, double* M, int ld, int T, double* logdet_part, int* info,
-                                   cudaStream_t st, CholLookahead& la) {
+                                   cudaStream_t st, CholLookahead& la, double* X = nullptr) {
     // K of the trailing update: wide panels only pay off when the trailing matrix is large (measured:
     // N = 16384 59.0 -> 56.6 ms with 8, N = 8192 12.3 -> 12.8 ms)
     const int PB = g_panel_blocks > 0 ? g_panel_blocks : (T >= 96 ? 8 : 4);
     const int NP = (T + PB - 1) / PB;
     if (NP > la.panels) return cudaErrorInvalidValue;
     const bool deep = g_lookahead_depth >= 2;
+    const int H = trtri_split_point(T);
+    const bool overlap = g_overlap_inverse && X != nullptr && H > 0 && NP > 1;
+    la.inv_pending = false;
     GPP_TRY(cudaEventRecord(la.fork, st));
     GPP_TRY(cudaStreamWaitEvent(la.side, la.fork, 0));
     // Depth-2 schedule.  U(p,c) = update of panel c's tile columns with panel p.
@@ -1000,6 +1019,13 @@ inline cudaError_t potrf_lookahead(double* A, double* M, int ld, int T, double* 
         GPP_TRY(panel_factor(A, M, ld, T, p0, pend, logdet_part, info, la.side));
         GPP_TRY(cudaEventRecord(la.ev_pf[p], la.side));
         if (pend >= T) break;
+        if (overlap && !la.inv_pending && pend >= H) {
+            // the first H tile columns of L are final: their share of L^-1 runs behind the rest of the factorisation
+            GPP_TRY(cudaStreamWaitEvent(la.inv, la.ev_pf[p], 0));
+            GPP_TRY(trtri_early(A, M, X, ld, T, la.inv));
+            GPP_TRY(cudaEventRecord(la.inv_done, la.inv));
+            la.inv_pending = true;
+        }
         const int nend = (pend + PB < T) ? pend + PB : T;
         if (last_ev >= 0) GPP_TRY(cudaStreamWaitEvent(la.side, la.ev_tu[last_ev], 0));
         GPP_TRY(trailing_update(A, ld, T, p0, pend, pend, nend, la.side));  // U(p,p+1)
@@ -1009,9 +1035,9 @@ inline cudaError_t potrf_lookahead(double* A, double* M, int ld, int T, double* 
                 const int n2end = (nend + PB < T) ? nend + PB : T;
                 GPP_TRY(trailing_update(A, ld, T, p0, pend, nend, n2end, st));  // U(p,p+2)
                 GPP_TRY(cudaEventRecord(la.ev_tu[p], st));
-                GPP_TRY(trailing_update(A, ld, T, p0, pend, n2end, T, st));     // U(p,p+3..)
+                GPP_TRY(trailing_update(A, ld, T, p0, pend, n2end, T, st, g_tu_max_ctas));  // U(p,p+3..)
             } else {
-                GPP_TRY(trailing_update(A, ld, T, p0, pend, nend, T, st));
+                GPP_TRY(trailing_update(A, ld, T, p0, pend, nend, T, st, g_tu_max_ctas));
                 GPP_TRY(cudaEventRecord(la.ev_tu[p], st));
             }
             last_ev = p;
@@ -1023,65 +1049,100 @@ inline cudaError_t potrf_lookahead(double* A, double* M, int ld, int T, double* 
 }
 
 // M (diagonal 128-blocks already hold L_kk^-1) <- L^-1 (lower); X is an N x N scratch.
-inline cudaError_t trtri_doubling(const double* L, double* M, double* X, int ld, int T, cudaStream_t st) {
-    for (int hb = 1; hb < T; hb *= 2) {
-        // groups of 2*hb blocks; first half [g0, g0+hb), second half [g0+hb, min(g0+2hb, T))
-        const int ngroups = (T + 2 * hb - 1) / (2 * hb);
-        int nb = 0, last_s2 = 0;  // groups with a non-empty second half
-        for (int gidx = 0; gidx < ngroups; gidx++) {
-            int s2 = T - (gidx * 2 * hb + hb);
-            if (s2 <= 0) break;
-            if (s2 > hb) s2 = hb;
-            nb++;
-            last_s2 = s2;
-        }
-        if (nb == 0) continue;
-        const long long zs = (long long)2 * hb * TILE * ld + (long long)2 * hb * TILE;  // next group, diagonal step
-        const long long off21 = (long long)hb * TILE * ld;                              // block (hb, 0) of the group
-        const long long off22 = (long long)hb * TILE * ld + (long long)hb * TILE;
-        {   // X21 = L21 * M11 ; M11 lower: k-blocks [tj, hb)
-            GemmOp op = gemm_default();
-            op.A = L + off21;
-            op.lda = ld;
-            op.a_zs = zs;
-            op.B = M;
-            op.ldb = ld;
-            op.b_zs = zs;
-            op.C = X + off21;
-            op.ldc = ld;
-            op.c_zs = zs;
-            op.tiles_m = hb;
-            op.tiles_m_last = last_s2;
-            op.tiles_n = hb;
-            op.klo_sel = KSEL_TJ;
-            op.klo_c = 0;
-            op.khi_sel = KSEL_CONST;
-            op.khi_c = hb;
-            GPP_TRY(launch_gemm(op, true, false, nb, st));
-        }
-        {   // M21 = -M22 * X21 ; M22 lower: k-blocks [0, ti+1)
-            GemmOp op = gemm_default();
-            op.A = M + off22;
-            op.lda = ld;
-            op.a_zs = zs;
-            op.B = X + off21;
-            op.ldb = ld;
-            op.b_zs = zs;
-            op.C = M + off21;
-            op.ldc = ld;
-            op.c_zs = zs;
-            op.tiles_m = hb;
-            op.tiles_m_last = last_s2;
-            op.tiles_n = hb;
-            op.klo_sel = KSEL_CONST;
-            op.klo_c = 0;
-            op.khi_sel = KSEL_TI;
-            op.khi_c = 1;
-            op.alpha = -1.0;
-            GPP_TRY(launch_gemm(op, true, false, nb, st));
-        }
+// One level of the recursive doubling on the groups [g_lo, g_hi) of 2*hb tiles each:
+//   X21 = L21 * M11 (part & 1), then M21 = -M22 * X21 (part & 2); groups are independent (batched launch).
+inline cudaError_t trtri_level(const double* L, double* M, double* X, int ld, int T, int hb, int g_lo, int g_hi,
+                               int part, cudaStream_t st, int max_ctas = 0) {
+    int nb = 0, last_s2 = 0;  // groups of the range with a non-empty second half
+    for (int gidx = g_lo; gidx < g_hi; gidx++) {
+        int s2 = T - (gidx * 2 * hb + hb);
+        if (s2 <= 0) break;
+        if (s2 > hb) s2 = hb;
+        nb++;
+        last_s2 = s2;
+    }
+    if (nb == 0) return cudaSuccess;
+    const long long zs = (long long)2 * hb * TILE * ld + (long long)2 * hb * TILE;  // next group, diagonal step
+    const long long base = (long long)g_lo * zs;
+    const long long off21 = base + (long long)hb * TILE * ld;                        // block (hb, 0) of the group
+    const long long off22 = base + (long long)hb * TILE * ld + (long long)hb * TILE;
+    if (part & 1) {   // X21 = L21 * M11 ; M11 lower: k-blocks [tj, hb)
+        GemmOp op = gemm_default();
+        op.A = L + off21;
+        op.lda = ld;
+        op.a_zs = zs;
+        op.B = M + base;
+        op.ldb = ld;
+        op.b_zs = zs;
+        op.C = X + off21;
+        op.ldc = ld;
+        op.c_zs = zs;
+        op.tiles_m = hb;
+        op.tiles_m_last = last_s2;
+        op.tiles_n = hb;
+        op.klo_sel = KSEL_TJ;
+        op.klo_c = 0;
+        op.khi_sel = KSEL_CONST;
+        op.khi_c = hb;
+        op.max_ctas = (nb == 1) ? max_ctas : 0;
+        GPP_TRY(launch_gemm(op, true, false, nb, st));
+    }
+    if (part & 2) {   // M21 = -M22 * X21 ; M22 lower: k-blocks [0, ti+1)
+        GemmOp op = gemm_default();
+        op.A = M + off22;
+        op.lda = ld;
+        op.a_zs = zs;
+        op.B = X + off21;
+        op.ldb = ld;
+        op.b_zs = zs;
+        op.C = M + off21;
+        op.ldc = ld;
+        op.c_zs = zs;
+        op.tiles_m = hb;
+        op.tiles_m_last = last_s2;
+        op.tiles_n = hb;
+        op.klo_sel = KSEL_CONST;
+        op.klo_c = 0;
+        op.khi_sel = KSEL_TI;
+        op.khi_c = 1;
+        op.alpha = -1.0;
+        op.max_ctas = (nb == 1) ? max_ctas : 0;
+        GPP_TRY(launch_gemm(op, true, false, nb, st));
     }
     return cudaSuccess;
+}
+
+inline cudaError_t trtri_doubling(const double* L, double* M, double* X, int ld, int T, cudaStream_t st) {
+    for (int hb = 1; hb < T; hb *= 2)
+        GPP_TRY(trtri_level(L, M, X, ld, T, hb, 0, (T + 2 * hb - 1) / (2 * hb), 3, st));
+    return cudaSuccess;
+}
+
+// Split of the same computation around H = largest power of two below T, so that the part that only needs the
+// first H tile columns of L can run while the factorisation is still working on the rest (where it is
+// latency-bound and leaves SMs idle):
+//   early (needs L[:, 0:H] final):  L11^-1 for the leading H tiles (all levels hb < H on the groups inside [0,H))
+//                                   and X21 = L[H:T, 0:H] * M11 (first half of the top level)
+//   late  (needs all of L):         the levels hb < H on the groups inside [H,T), then M21 = -M22 * X21
+inline int trtri_split_point(int T) {
+    int H = 1;
+    while (H * 2 < T) H *= 2;
+    return (T >= 2) ? H : 0;
+}
+inline cudaError_t trtri_early(const double* L, double* M, double* X, int ld, int T, cudaStream_t st) {
+    const int H = trtri_split_point(T);
+    if (H == 0) return cudaSuccess;
+    for (int hb = 1; hb < H; hb *= 2)
+        GPP_TRY(trtri_level(L, M, X, ld, T, hb, 0, H / (2 * hb), 3, st, g_inv_max_ctas));
+    if (g_overlap_inverse == 2) return cudaSuccess;  // experiment: leave X21 to the late part
+    return trtri_level(L, M, X, ld, T, H, 0, 1, 1, st, g_inv_max_ctas);
+}
+inline cudaError_t trtri_late(const double* L, double* M, double* X, int ld, int T, cudaStream_t st) {
+    const int H = trtri_split_point(T);
+    if (H == 0) return cudaSuccess;
+    for (int hb = 1; hb < H; hb *= 2)
+        GPP_TRY(trtri_level(L, M, X, ld, T, hb, H / (2 * hb), (T + 2 * hb - 1) / (2 * hb), 3, st));
+    return trtri_level(L, M, X, ld, T, H, 0, 1, g_overlap_inverse == 2 ? 3 : 2, st);
 }
 
 // Kinv = M^T M (full symmetric storage); M lower: k-blocks [ti, T)

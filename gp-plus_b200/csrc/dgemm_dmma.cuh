@@ -75,6 +75,9 @@ struct GemmOp {
     int epilogue;                // Epilogue
     double* rowsq;               // EPI_ROWSQ: rowsq[tj * rowsq_ld + global_row] = sum_n acc[row][n]^2
     int rowsq_ld;
+    int total_ctas;              // set by launch_gemm: work items along x; CTAs stride over them (persistent when
+                                 // the grid is smaller than this)
+    int max_ctas;                // 0 = one CTA per work item; otherwise cap on gridDim.x (leaves SMs to other streams)
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -127,8 +130,9 @@ __global__ void __launch_bounds__(GemmCfg<BM>::THREADS, GemmCfg<BM>::MIN_CTAS) d
     const int tid = threadIdx.x;
     const int z = blockIdx.y;
     const int tm = (z == (int)gridDim.y - 1) ? op.tiles_m_last : op.tiles_m;
-    const int half = (SPLIT == 1) ? 0 : (int)(blockIdx.x % SPLIT);
-    const int tile_id = (SPLIT == 1) ? (int)blockIdx.x : (int)(blockIdx.x / SPLIT);
+  for (int work = blockIdx.x; work < op.total_ctas; work += gridDim.x) {
+    const int half = (SPLIT == 1) ? 0 : (work % SPLIT);
+    const int tile_id = (SPLIT == 1) ? work : (work / SPLIT);
     const int r0 = half * BM;  // first row of this CTA inside its 128-row tile
 
     // Tile rasterisation: super-rows of GS tile rows, column-major inside a super-row, so that the ~150 tiles in
@@ -156,15 +160,15 @@ __global__ void __launch_bounds__(GemmCfg<BM>::THREADS, GemmCfg<BM>::MIN_CTAS) d
             tj = r0g + c;
             ti = r0g + c + local;
         }
-        if (ti >= tm) return;
+        if (ti >= tm) continue;
     } else {
         const int r0g = (tile_id / (GS * op.tiles_n)) * GS;
         const int R = (op.tiles_m - r0g < GS) ? (op.tiles_m - r0g) : GS;
         const int local = tile_id - r0g * op.tiles_n;
         tj = local / R;
         ti = r0g + (local - tj * R);
-        if (ti >= tm) return;
-        if (op.lower_filter && (ti + op.lower_off < tj)) return;
+        if (ti >= tm) continue;
+        if (op.lower_filter && (ti + op.lower_off < tj)) continue;
     }
 
     int klo = op.klo_c + (op.klo_sel == KSEL_TI ? ti : (op.klo_sel == KSEL_TJ ? tj : 0));
@@ -261,7 +265,8 @@ __global__ void __launch_bounds__(GemmCfg<BM>::THREADS, GemmCfg<BM>::MIN_CTAS) d
             double s = red[tid] + red[BM + tid];
             op.rowsq[(long long)tj * op.rowsq_ld + (long long)z * op.c_zs + (long long)ti * TILE + r0 + tid] = s;
         }
-        return;
+        __syncthreads();  // `red` aliases the first pipeline stage of the next work item
+        continue;
     }
 
     double* Cg = op.C + (long long)z * op.c_zs + ((long long)ti * TILE + r0) * op.ldc + (long long)tj * TILE;
@@ -289,12 +294,17 @@ __global__ void __launch_bounds__(GemmCfg<BM>::THREADS, GemmCfg<BM>::MIN_CTAS) d
             }
         }
     }
+  }  // work items
 }
 
 template <int BM>
-inline cudaError_t launch_gemm_bm(const GemmOp& op, bool a_kc, bool b_kc, int nt, int nbatch, cudaStream_t st) {
+inline cudaError_t launch_gemm_bm(const GemmOp& op_in, bool a_kc, bool b_kc, int nt, int nbatch, cudaStream_t st) {
     using Cfg = GemmCfg<BM>;
-    dim3 grid(nt * (TILE / BM), nbatch), block(Cfg::THREADS);
+    GemmOp op = op_in;
+    op.total_ctas = nt * (TILE / BM);
+    int gx = op.total_ctas;
+    if (op.max_ctas > 0 && gx > op.max_ctas) gx = op.max_ctas;
+    dim3 grid(gx, nbatch), block(Cfg::THREADS);
     if (a_kc && b_kc) dgemm_dmma_kernel<true, true, BM><<<grid, block, Cfg::SMEM_BYTES, st>>>(op);
     else if (a_kc && !b_kc) dgemm_dmma_kernel<true, false, BM><<<grid, block, Cfg::SMEM_BYTES, st>>>(op);
     else if (!a_kc && !b_kc) dgemm_dmma_kernel<false, false, BM><<<grid, block, Cfg::SMEM_BYTES, st>>>(op);

@@ -211,7 +211,12 @@ extern "C" int gpp_create(const gpp_problem* p, int device, gpp_handle** out) {
             if (cudaSetDeviceFlags(cudaDeviceScheduleBlockingSync) != cudaSuccess) cudaGetLastError();
         }
     }
-    CKH(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+    {
+        // three priority classes: panel chain (side stream, highest) > this stream > overlapped inverse (lowest)
+        int lo = 0, hi = 0;
+        CKH(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CKH(cudaStreamCreateWithPriority(&h->st, cudaStreamNonBlocking, (lo + hi) / 2));
+    }
     for (int i = 0; i < EV_COUNT; i++) CKH(cudaEventCreate(&h->ev[i]));
     CKH(chol_set_attributes());
     CKH(cov_set_attributes());
@@ -221,6 +226,9 @@ extern "C" int gpp_create(const gpp_problem* p, int device, gpp_handle** out) {
         if ((e = getenv("GPP_CHOL")) != nullptr) h->use_lookahead = strcmp(e, "blocked") != 0;
         if ((e = getenv("GPP_LEAF")) != nullptr) g_leaf_version = std::max(1, std::min(4, atoi(e)));
         if ((e = getenv("GPP_PANEL")) != nullptr) g_panel_blocks = atoi(e);
+        if ((e = getenv("GPP_OVERLAP_INV")) != nullptr) g_overlap_inverse = atoi(e);
+        if ((e = getenv("GPP_TU_CTAS")) != nullptr) g_tu_max_ctas = atoi(e);
+        if ((e = getenv("GPP_INV_CTAS")) != nullptr) g_inv_max_ctas = atoi(e);
         if ((e = getenv("GPP_GEMM_BM")) != nullptr) g_gemm_bm = atoi(e) == 64 ? 64 : 128;
         h->use_graph = h->T <= 16;  // N <= 2048: an evaluation is a chain of ~25-100 tiny launches
         if ((e = getenv("GPP_GRAPH")) != nullptr) h->use_graph = atoi(e) != 0;
@@ -403,7 +411,7 @@ static int stage_factor(gpp_handle* h) {
     CK(launch_cov(ca, h->kernel, h->st));
     mark(h, EV_COV);
     if (h->use_lookahead)
-        CK(potrf_lookahead(h->A, h->M, (int)h->np, h->T, h->logdet_part, h->info, h->st, h->la));
+        CK(potrf_lookahead(h->A, h->M, (int)h->np, h->T, h->logdet_part, h->info, h->st, h->la, h->S));
     else
         CK(potrf_blocked(h->A, h->M, (int)h->np, h->T, h->logdet_part, h->info, h->st));
     mark(h, EV_CHOL);
@@ -412,7 +420,14 @@ static int stage_factor(gpp_handle* h) {
 
 // M <- L^-1, v = M r, alpha = M^T v
 static int stage_inverse_solve(gpp_handle* h) {
-    CK(trtri_doubling(h->A, h->M, h->S, (int)h->np, h->T, h->st));
+    if (h->use_lookahead && h->la.inv_pending) {
+        // the leading part of L^-1 was started behind the factorisation (trtri_early): join it, finish the rest
+        CK(cudaStreamWaitEvent(h->st, h->la.inv_done, 0));
+        h->la.inv_pending = false;
+        CK(trtri_late(h->A, h->M, h->S, (int)h->np, h->T, h->st));
+    } else {
+        CK(trtri_doubling(h->A, h->M, h->S, (int)h->np, h->T, h->st));
+    }
     mark(h, EV_TRTRI);
     trmv_lower_kernel<<<(int)(h->np / 8), 256, 0, h->st>>>(h->M, h->np, h->r, (int)h->np, h->v);
     CK(cudaGetLastError());
