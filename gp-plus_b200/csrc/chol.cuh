@@ -6,14 +6,16 @@
 // multiple of 128 (padded rows/cols carry an identity block, so they change neither the
 // factor, log|K| nor the solves).
 //
-//   1. potrf: right-looking, two-level blocking.  Inside a panel of PANEL_BLOCKS 128-columns:
+//   1. potrf: right-looking with look-ahead.  A panel (4 or 8 tile columns, factored recursively down to pairs)
+//      runs on a high-priority side stream:
 //        leaf  (one CTA): L_kk = chol(A_kk) and L_kk^-1 (written into the diagonal block of M)
 //        TRSM  (DMMA GEMM, K=128): A_ik <- A_ik * L_kk^-T  via the explicit 128x128 inverse
-//        panel update (DMMA GEMM, K=128) of the remaining panel columns
-//      then one trailing SYRK with K = 128*PANEL_BLOCKS (DMMA GEMM, lower tiles only).
+//        in-panel updates (DMMA GEMM, K = 128 .. panel/2)
+//      while the trailing SYRK of the previous panel (DMMA GEMM, K = panel width, lower tiles) runs on the main stream.
 //   2. trtri: M = L^-1 by recursive doubling.  With the diagonal 128-blocks already inverted,
 //      level h combines aligned groups of h blocks:  M21 = -M22 * (L21 * M11); every group of
-//      a level is independent, so a level is two batched GEMM launches (ceil(log2 T) levels).
+//      a level is independent, so a level is two batched GEMM launches (ceil(log2 T) levels).  The part that
+//      only needs the leading tile columns of L starts behind the factorisation on a third stream.
 //   3. lauum: K^-1 = M^T M, one launch over the lower tiles, mirrored into the upper triangle.
 #pragma once
 #include <vector>
@@ -26,9 +28,8 @@ constexpr int LEAF_THREADS = 256;
 constexpr int LB = 32;     // sub-block edge inside a 128x128 leaf
 constexpr int LLD = 132;   // smem leading dimension: 132 = 4 (mod 16) keeps every DMMA fragment load conflict-free
 constexpr int TLD = 36;    // per-warp scratch leading dimension (same residue)
-constexpr int LEAF_SMEM_BYTES = (TILE * LLD + TILE + 3 * LB * TLD) * 8;
 constexpr int PANEL_BLOCKS = 4;   // leaf-level panel: in-panel updates run at K = 128
-inline int g_panel_base = 2;       // widest piece factored with K = 128 in-panel updates (recursion stops here)
+constexpr int PANEL_BASE = 2;      // widest piece factored with K = 128 in-panel updates (the recursion stops here)
 inline int g_panel_blocks = 0;     // look-ahead panel width in 128-columns; 0 = by size (8 from N = 12288, else 4)
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -57,193 +58,20 @@ __device__ __forceinline__ void acc_zero(double (&acc)[4][4][2]) {
         for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 }
 
-// One warp factors the 32x32 diagonal sub-block at offset b (lane i owns row i in registers, pivots travel by
-// shuffle) and inverts the factor (lane c owns column c of the inverse; L is re-read from shared memory with
-// warp-uniform addresses).  On exit the lower triangle of the sub-block holds L, its strict upper triangle holds
-// (L^-1)^T and xd[b+i] = 1/L_ii.  log L_jj is accumulated as (mantissa product, exponent sum): one log per block.
-__device__ __forceinline__ void warp_potrf_inv32(double* S, double* xd, int b, int lane, int& bad, double& logacc) {
-    double mydinv = 0.0;
-    {
-        double a[LB];
-#pragma unroll
-        for (int k = 0; k < LB; k++) a[k] = (k <= lane) ? S[(b + lane) * LLD + b + k] : 0.0;
-        double mant = 1.0;
-        int esum = 0;
-#pragma unroll
-        for (int j = 0; j < LB; j++) {
-            const double d = __shfl_sync(FULL, a[j], j);
-            if (!(d > 0.0) && bad == 0) bad = (d != d) ? 2 : 1;  // the first failing pivot decides
-            const double l = sqrt(d);
-            const double inv = 1.0 / l;
-            int ex;
-            mant *= frexp(l, &ex);
-            esum += ex;
-            if (lane == j) mydinv = inv;
-            const double lij = (lane == j) ? l : ((lane > j) ? a[j] * inv : 0.0);
-            a[j] = lij;
-#pragma unroll
-            for (int k = j + 1; k < LB; k++) {
-                const double lkj = __shfl_sync(FULL, lij, k);
-                if (lane >= k) a[k] = fma(-lij, lkj, a[k]);
-            }
-        }
-        logacc += log(mant) + (double)esum * 0.6931471805599453;
-#pragma unroll
-        for (int k = 0; k < LB; k++)
-            if (k <= lane) S[(b + lane) * LLD + b + k] = a[k];
-        xd[b + lane] = mydinv;
-    }
-    __syncwarp();
-    // X = L^-1: X[i][c] = -(sum_{k=c}^{i-1} L[i][k] X[k][c]) / L[i][i]
-    double x[LB];
-#pragma unroll
-    for (int i = 0; i < LB; i++) {
-        double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-        for (int k = 0; k < i; k++) {
-            const double lik = S[(b + i) * LLD + b + k];
-            if (k & 1) s1 = fma(lik, x[k], s1);
-            else s0 = fma(lik, x[k], s0);
-        }
-        const double di = xd[b + i];
-        x[i] = (lane == i) ? di : ((lane < i) ? -(s0 + s1) * di : 0.0);
-    }
-#pragma unroll
-    for (int k = 0; k < LB; k++)
-        if (k > lane) S[(b + lane) * LLD + b + k] = x[k];
-}
-
-// info[0]: 0 ok, 1 = non-positive pivot, 2 = NaN pivot.  logdet_part[kb] = sum_j log L_jj of block kb.
-// Blocked (4 x 32) right-looking factorisation of the 128x128 diagonal block kb of A plus its explicit inverse
-// (written to the diagonal block of M): diagonal sub-blocks by one warp in registers, every 32^3 product
-// (TRSM through the sub-block inverse, SYRK updates, block forward substitution of the inverse) by one warp on DMMA.
-__global__ void __launch_bounds__(LEAF_THREADS, 1)
-leaf_potrf_trinv_kernel(double* A, int ld, int kb, double* M, double* logdet_part, int* info) {
-    extern __shared__ __align__(16) double sm[];
-    double* S = sm;                 // [128][LLD]: lower = L, strict upper = (L^-1)^T
-    double* xd = sm + TILE * LLD;   // [128] 1/L_jj
-    double* Tall = xd + TILE;       // [3][32][TLD] per-warp scratch
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = lane >> 2, t = lane & 3;
-    double* Ab = A + (long long)kb * TILE * ld + (long long)kb * TILE;
-    double* Mb = M + (long long)kb * TILE * ld + (long long)kb * TILE;
-
-    for (int idx = tid; idx < TILE * TILE; idx += LEAF_THREADS) {
-        int i = idx >> 7, j = idx & 127;
-        S[i * LLD + j] = (j <= i) ? Ab[(long long)i * ld + j] : 0.0;
-    }
-    __syncthreads();
-
-    int bad = 0;
-    double logacc = 0.0;
-    double acc[4][4][2];
-    for (int q = 0; q < 4; q++) {
-        const int b = q * LB;
-        if (warp == 0) warp_potrf_inv32(S, xd, b, lane, bad, logacc);
-        __syncthreads();
-        if (warp < 3 - q) {  // TRSM: L_ib,q = A_ib,q * X_q^T
-            const int r0 = (q + 1 + warp) * LB;
-            acc_zero(acc);
-            warp_mm32(acc, [&](int r, int k) { return S[(r0 + r) * LLD + b + k]; },
-                      [&](int k, int c) { return k < c ? S[(b + k) * LLD + b + c] : (k == c ? xd[b + c] : 0.0); }, g, t);
-            __syncwarp();
-#pragma unroll
-            for (int mi = 0; mi < 4; mi++)
-#pragma unroll
-                for (int ni = 0; ni < 4; ni++)
-#pragma unroll
-                    for (int e = 0; e < 2; e++) S[(r0 + mi * 8 + g) * LLD + b + ni * 8 + 2 * t + e] = acc[mi][ni][e];
-        }
-        __syncthreads();
-        {   // SYRK: A_ib,jb -= L_ib,q L_jb,q^T for q < jb <= ib <= 3 (one warp per block pair)
-            const int m = 3 - q;  // remaining block rows
-            if (warp < m * (m + 1) / 2) {
-                int u = 0, w = warp;
-                while (w > u) { w -= u + 1; u++; }  // warp -> (u, w), w <= u
-                const int i0 = (q + 1 + u) * LB, j0 = (q + 1 + w) * LB;
-                acc_zero(acc);
-                warp_mm32(acc, [&](int r, int k) { return S[(i0 + r) * LLD + b + k]; },
-                          [&](int k, int c) { return S[(j0 + c) * LLD + b + k]; }, g, t);
-#pragma unroll
-                for (int mi = 0; mi < 4; mi++)
-#pragma unroll
-                    for (int ni = 0; ni < 4; ni++)
-#pragma unroll
-                        for (int e = 0; e < 2; e++) {
-                            const int r = mi * 8 + g, c = ni * 8 + 2 * t + e;
-                            if (i0 != j0 || c <= r) S[(i0 + r) * LLD + j0 + c] -= acc[mi][ni][e];
-                        }
-            }
-        }
-        __syncthreads();
-    }
-    if (tid == 0) {
-        logdet_part[kb] = logacc;
-        if (bad && *info == 0) atomicOr(info, bad);  // leaves run in sequence: an earlier failure wins
-    }
-
-    // off-diagonal 32-blocks of X = L^-1 by block forward substitution, one block-diagonal distance at a time:
-    //   X_ij = -X_ii * sum_{k=j}^{i-1} L_ik X_kj        (X[r][c] is stored at S[c][r])
-    for (int dist = 1; dist < 4; dist++) {
-        if (warp < 4 - dist) {
-            const int j = warp, i = warp + dist;
-            double* T = Tall + warp * LB * TLD;
-            acc_zero(acc);
-            for (int k = j; k < i; k++) {
-                if (k == j) {
-                    warp_mm32(acc, [&](int r, int kk) { return S[(i * LB + r) * LLD + k * LB + kk]; },
-                              [&](int kk, int n) {
-                                  return n < kk ? S[(j * LB + n) * LLD + j * LB + kk] : (n == kk ? xd[j * LB + kk] : 0.0);
-                              }, g, t);
-                } else {
-                    warp_mm32(acc, [&](int r, int kk) { return S[(i * LB + r) * LLD + k * LB + kk]; },
-                              [&](int kk, int n) { return S[(j * LB + n) * LLD + k * LB + kk]; }, g, t);
-                }
-            }
-#pragma unroll
-            for (int mi = 0; mi < 4; mi++)
-#pragma unroll
-                for (int ni = 0; ni < 4; ni++)
-#pragma unroll
-                    for (int e = 0; e < 2; e++) T[(mi * 8 + g) * TLD + ni * 8 + 2 * t + e] = acc[mi][ni][e];
-            __syncwarp();
-            acc_zero(acc);
-            warp_mm32(acc, [&](int r, int kk) {
-                          return kk < r ? S[(i * LB + kk) * LLD + i * LB + r] : (kk == r ? xd[i * LB + r] : 0.0);
-                      },
-                      [&](int kk, int n) { return T[kk * TLD + n]; }, g, t);
-#pragma unroll
-            for (int mi = 0; mi < 4; mi++)
-#pragma unroll
-                for (int ni = 0; ni < 4; ni++)
-#pragma unroll
-                    for (int e = 0; e < 2; e++)
-                        S[(j * LB + ni * 8 + 2 * t + e) * LLD + i * LB + mi * 8 + g] = -acc[mi][ni][e];
-        }
-        __syncthreads();
-    }
-
-    for (int idx = tid; idx < TILE * TILE; idx += LEAF_THREADS) {
-        int i = idx >> 7, c = idx & 127;
-        if (c <= i) Ab[(long long)i * ld + c] = S[i * LLD + c];
-        Mb[(long long)i * ld + c] = (c < i) ? S[c * LLD + i] : ((c == i) ? xd[i] : 0.0);
-    }
-}
-
-
 // ---------------------------------------------------------------------------------------------
-// Leaf, second generation.  Same contract as leaf_potrf_trinv_kernel (A_kk -> L_kk in place, M_kk <- L_kk^-1,
-// logdet_part[kb], info) with a much shorter critical path:
-//   * the 32x32 diagonal factorisation broadcasts each finished column through shared memory (one 16-byte
-//     uniform load feeds two updates) instead of two shuffles per update, and uses rsqrt + one Newton step
-//     instead of sqrt followed by a division;
-//   * the rows below a diagonal sub-block are solved by substitution, one lane per row, straight from the
-//     transposed factor, so they do not wait for the sub-block inverse;
-//   * the sub-block inverses are computed by a dedicated warp (named barriers 2..5) while warps 0-6 continue
-//     with the factorisation (named barrier 1); the diagonal update that gates the next sub-block is done by
-//     the factorising warp itself, so only two CTA-wide (224-thread) barriers remain per sub-block;
-//   * the off-diagonal 32-blocks of the inverse are assembled in four rounds (T = X_ii L_ik first, then the
-//     block columns in parallel) instead of nine dependent 32^3 products.
+// Leaf: A_kk -> L_kk in place, M_kk <- L_kk^-1, logdet_part[kb] = sum log L_jj, info (1 = non-positive pivot,
+// 2 = NaN pivot; the first failure of a factorisation wins).  One CTA, latency-bound, so everything is about the
+// length of the dependency chain:
+//   * each 32x32 diagonal sub-block is factored by one warp in registers, four columns at a time: the 4x4 pivot
+//     block is broadcast by shuffle and factored redundantly by every lane, each lane solves its own row against
+//     it, and one shared-memory exchange per micro-panel feeds the (unpredicated) rank-4 update; rsqrt + one
+//     Newton step replaces sqrt and division (measured on B200: DFMA 8 cycles, rsqrt 74, sqrt 98, div 79);
+//   * the rows below a diagonal sub-block are solved by substitution, one lane per row, from the transposed factor;
+//   * the SYRK that gates the next sub-block runs as four 8-row strips on warps 0-3 (named barrier 6), the other
+//     block pairs on the remaining warps of the main group (named barrier 1, warps 0-6);
+//   * warp 7 inverts each sub-block as soon as it is final (named barriers 2..5) by right-looking substitution
+//     and stores it; warp 3 streams finished block columns of L out; the off-diagonal blocks of the inverse are
+//     assembled in four rounds (T = X_ii L_ik first, then the block columns in parallel).
 constexpr int LTLD = 34;                               // transposed-factor row stride (even: 16-byte rows)
 constexpr int L2_S = TILE * LLD;                       // S      [128][LLD]
 constexpr int L2_XD = TILE;                            // xd     [128]  1/L_jj
@@ -258,54 +86,6 @@ __device__ __forceinline__ void named_bar_sync(int id, int count) {
 }
 __device__ __forceinline__ void named_bar_arrive(int id, int count) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-
-// One warp: in-register right-looking Cholesky of the 32x32 block at (b,b) of S.  Lane i owns row i.
-// Writes L (row-major) back to S, L^T to LT (LT[j][i] = L_ij) and 1/L_jj to xd.
-__device__ __forceinline__ void warp_potrf32_v2(double* S, double* xd, double* LT, int b, int lane, int& bad,
-                                                double& mant, int& esum) {
-    double a[LB];
-    double* row = S + (b + lane) * LLD + b;
-#pragma unroll
-    for (int k = 0; k < LB; k += 2) {
-        const double2 v = *reinterpret_cast<const double2*>(row + k);
-        a[k] = (k <= lane) ? v.x : 0.0;
-        a[k + 1] = (k + 1 <= lane) ? v.y : 0.0;
-    }
-    double mydinv = 0.0;
-#pragma unroll
-    for (int j = 0; j < LB; j++) {
-        const double d = __shfl_sync(FULL, a[j], j);
-        if (!(d > 0.0) && bad == 0) bad = (d != d) ? 2 : 1;  // the first failing pivot decides
-        double rs = rsqrt(d);
-        double l = d * rs;
-        l = fma(fma(-l, l, d), 0.5 * rs, l);   // sqrt(d), one Newton step on top of d * rsqrt(d)
-        rs = fma(fma(-l, rs, 1.0), rs, rs);    // 1 / l
-        int ex;
-        mant *= frexp(l, &ex);
-        esum += ex;
-        if (lane == j) mydinv = rs;
-        const double lij = (lane == j) ? l : ((lane > j) ? a[j] * rs : 0.0);
-        a[j] = lij;
-        LT[j * LTLD + lane] = lij;
-        __syncwarp();
-#pragma unroll
-        for (int k = (j + 1) & ~1; k < LB; k += 2) {
-            const double2 lk = *reinterpret_cast<const double2*>(LT + j * LTLD + k);
-            if (k > j) a[k] = (lane >= k) ? fma(-lij, lk.x, a[k]) : a[k];
-            a[k + 1] = (lane >= k + 1) ? fma(-lij, lk.y, a[k + 1]) : a[k + 1];
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < LB; k += 2) {
-        if (k <= lane) {
-            double2 v;
-            v.x = a[k];
-            v.y = (k + 1 <= lane) ? a[k + 1] : 0.0;
-            *reinterpret_cast<double2*>(row + k) = v;
-        }
-    }
-    xd[b + lane] = mydinv;
 }
 
 // One warp: rows row0..row0+31 of the block column b: x <- x * L_bb^-T by substitution (lane = row).
@@ -339,28 +119,7 @@ __device__ __forceinline__ void warp_trsm_sub32(double* S, const double* xd, con
     }
 }
 
-// One warp: X = L_bb^-1 (lane c owns column c), written row-major to Xd[32][TLD] (zeros above the diagonal).
-__device__ __forceinline__ void warp_trinv32_v2(const double* S, const double* xd, double* Xd, int b, int lane) {
-    double x[LB];
-#pragma unroll
-    for (int i = 0; i < LB; i++) {
-        double s0 = 0.0, s1 = 0.0;
-        const double* Li = S + (b + i) * LLD + b;
-#pragma unroll
-        for (int k = 0; k + 1 < i; k += 2) {
-            const double2 l2 = *reinterpret_cast<const double2*>(Li + k);
-            s0 = fma(l2.x, x[k], s0);
-            s1 = fma(l2.y, x[k + 1], s1);
-        }
-        if (i & 1) s0 = fma(Li[i - 1], x[i - 1], s0);
-        const double di = xd[b + i];
-        x[i] = (lane == i) ? di : ((lane < i) ? -(s0 + s1) * di : 0.0);
-        Xd[i * TLD + lane] = x[i];
-    }
-}
-
-
-// Third-generation 32x32 diagonal factorisation: four columns at a time.  The 4x4 pivot block is broadcast by
+// 32x32 diagonal factorisation by one warp (lane i owns row i), four columns at a time.  The 4x4 pivot block is broadcast by
 // shuffle and factored redundantly by every lane (no communication inside the micro-panel), each lane then
 // solves its own row against it, and one shared-memory exchange per micro-panel feeds the rank-4 update of the
 // remaining columns.  Updates are not predicated: entries above the diagonal hold bounded garbage that is
@@ -372,7 +131,7 @@ __device__ __forceinline__ void warp_trinv32_v2(const double* S, const double* x
     l = fma(fma(-l, l, (d)), 0.5 * rs, l);                        \
     rs = fma(fma(-l, rs, 1.0), rs, rs);
 
-__device__ __forceinline__ void warp_potrf32_v3(double* S, double* xd, double* LT, int b, int lane, int& bad,
+__device__ __forceinline__ void warp_potrf32(double* S, double* xd, double* LT, int b, int lane, int& bad,
                                                 double& mant, int& esum) {
     double a[LB];
     double* row = S + (b + lane) * LLD + b;
@@ -481,7 +240,7 @@ __device__ __forceinline__ void warp_syrk_strip8(double* S, int i0, int b, int w
 
 // One warp: X = L_bb^-1 by right-looking substitution on the identity (lane c owns column c): the dependent
 // chain per row is one multiply and one FMA instead of a half-row dot product.  LT[j][i] = L_ij.
-__device__ __forceinline__ void warp_trinv32_v3(const double* LT, const double* xd, double* Xd, int b, int lane) {
+__device__ __forceinline__ void warp_trinv32(const double* LT, const double* xd, double* Xd, int b, int lane) {
     double x[LB];
 #pragma unroll
     for (int r = 0; r < LB; r++) x[r] = (r == lane) ? 1.0 : 0.0;
@@ -519,9 +278,8 @@ __device__ __forceinline__ void acc_store32(double* dst, int ldd, const double (
 }
 
 // prof (optional): clock64 stamps written by thread 0 / lane 0 of the inverse warp
-template <int GEN>
 __global__ void __launch_bounds__(LEAF_THREADS, 1)
-leaf_potrf_trinv_v2_kernel(double* A, int ld, int kb, double* M, double* logdet_part, int* info, long long* prof) {
+leaf_potrf_trinv_kernel(double* A, int ld, int kb, double* M, double* logdet_part, int* info, long long* prof) {
     extern __shared__ __align__(16) double sm[];
     double* S = sm;
     double* xd = S + L2_S;
@@ -550,14 +308,10 @@ leaf_potrf_trinv_v2_kernel(double* A, int ld, int kb, double* M, double* logdet_
         // inverse warp: X_qq as soon as L_qq is final
         for (int q = 0; q < 4; q++) {
             named_bar_sync(2 + q, 64);
-            if (GEN >= 4) {
-                warp_trinv32_v3(LT + q * LB * LTLD, xd, Xd + q * LB * TLD, q * LB, lane);
-                __syncwarp();
-                // the diagonal sub-block of the inverse is final: store it now, off the tail
-                warp_store_rows32(Xd + q * LB * TLD, TLD, Mb + (long long)(q * LB) * ld + q * LB, ld, 0, LB, lane);
-            } else {
-                warp_trinv32_v2(S, xd, Xd + q * LB * TLD, q * LB, lane);
-            }
+            warp_trinv32(LT + q * LB * LTLD, xd, Xd + q * LB * TLD, q * LB, lane);
+            __syncwarp();
+            // the diagonal sub-block of the inverse is final: store it now, off the tail
+            warp_store_rows32(Xd + q * LB * TLD, TLD, Mb + (long long)(q * LB) * ld + q * LB, ld, 0, LB, lane);
         }
         if (prof && lane == 0) prof[15] = clock64();
     } else {
@@ -566,8 +320,7 @@ leaf_potrf_trinv_v2_kernel(double* A, int ld, int kb, double* M, double* logdet_
         for (int q = 0; q < 4; q++) {
             const int b = q * LB;
             if (warp == 0) {
-                if (GEN >= 3) warp_potrf32_v3(S, xd, LT + q * LB * LTLD, b, lane, bad, mant, esum);
-                else warp_potrf32_v2(S, xd, LT + q * LB * LTLD, b, lane, bad, mant, esum);
+                warp_potrf32(S, xd, LT + q * LB * LTLD, b, lane, bad, mant, esum);
                 __threadfence_block();
                 named_bar_arrive(2 + q, 64);
             }
@@ -577,7 +330,7 @@ leaf_potrf_trinv_v2_kernel(double* A, int ld, int kb, double* M, double* logdet_
             if (warp >= 1 && warp <= 3 - q) warp_trsm_sub32(S, xd, LT + q * LB * LTLD, (q + warp) * LB, b, lane);
             named_bar_sync(1, 224);
             GPP_STAMP(3 + 3 * q)
-            if (GEN >= 3) {
+            {
                 // SYRK: the next diagonal block (it gates the next factorisation) in four 8-row strips on warps 0-3,
                 // the other block pairs on warps 4,5,6,1,2 in that order
                 const int i0d = (q + 1) * LB;
@@ -585,7 +338,7 @@ leaf_potrf_trinv_v2_kernel(double* A, int ld, int kb, double* M, double* logdet_
                     warp_syrk_strip8(S, i0d, b, warp, g, t);
                     named_bar_sync(6, 128);
                 }
-                if (GEN >= 4 && warp == 3) {
+                if (warp == 3) {
                     // block column q of L is final (diagonal sub-block after the factorisation, the rows below it
                     // after the substitution): stream it out while the other warps update the trailing blocks
                     for (int r = b; r < TILE; r++) {
@@ -614,28 +367,6 @@ leaf_potrf_trinv_v2_kernel(double* A, int ld, int kb, double* M, double* logdet_
                             v.y -= acc[mi][ni][1];
                             *p2 = v;
                         }
-                }
-            } else {   // SYRK: A_uw -= L_uq L_wq^T, q < w <= u <= 3; pair 0 = the next diagonal block, owned by warp 0
-                const int m = 3 - q;
-                if (warp < m * (m + 1) / 2) {
-                    int u = 0, w = warp;
-                    while (w > u) { w -= u + 1; u++; }
-                    const int i0 = (q + 1 + u) * LB, j0 = (q + 1 + w) * LB;
-                    acc_zero(acc);
-                    warp_mm32(acc, [&](int r, int k) { return S[(i0 + r) * LLD + b + k]; },
-                              [&](int k, int c) { return S[(j0 + c) * LLD + b + k]; }, g, t);
-#pragma unroll
-                    for (int mi = 0; mi < 4; mi++)
-#pragma unroll
-                        for (int ni = 0; ni < 4; ni++) {
-                            const int r = mi * 8 + g, c = ni * 8 + 2 * t;
-                            double2* p2 = reinterpret_cast<double2*>(S + (i0 + r) * LLD + j0 + c);
-                            double2 v = *p2;
-                            v.x -= acc[mi][ni][0];
-                            v.y -= acc[mi][ni][1];
-                            *p2 = v;
-                        }
-                    __syncwarp();
                 }
             }
             GPP_STAMP(4 + 3 * q)
@@ -700,7 +431,7 @@ leaf_potrf_trinv_v2_kernel(double* A, int ld, int kb, double* M, double* logdet_
     GPP_STAMP(12)
 #undef GPP_T
 
-    if (GEN >= 4) {
+    {
         // everything except the last diagonal sub-block of L and the six off-diagonal sub-blocks of the inverse
         // has already been stored; 7 block copies over 8 warps
         if (warp == 7) {
@@ -713,28 +444,6 @@ leaf_potrf_trinv_v2_kernel(double* A, int ld, int kb, double* M, double* logdet_
             while (j >= i) { j -= i; i++; }  // warp -> (i,j): (1,0) (2,0) (2,1) (3,0) (3,1) (3,2)
             warp_store_rows32(GPP_XOFF(i, j), LLD, Mb + (long long)(i * LB) * ld + j * LB, ld, 0, LB, lane);
         }
-    } else {
-    // write back: L (lower) to A_kk, X (lower, zeros above) to M_kk; 16-byte coalesced stores
-    for (int idx = tid; idx < TILE * (TILE / 2); idx += LEAF_THREADS) {
-        const int i = idx >> 6, c = (idx & 63) * 2;
-        const int bi = i >> 5, bc = c >> 5;
-        if (c <= i) {
-            double2 v = *reinterpret_cast<const double2*>(S + i * LLD + c);
-            if (c + 1 > i) v.y = Ab[(long long)i * ld + c + 1];  // keep the entry above the diagonal untouched
-            *reinterpret_cast<double2*>(Ab + (long long)i * ld + c) = v;
-        }
-        double2 x;
-        if (bc > bi) {
-            if (GEN >= 3) continue;  // M is zero-initialised once and nothing ever writes above its diagonal blocks
-            x.x = 0.0;
-            x.y = 0.0;
-        } else if (bc == bi) {
-            x = *reinterpret_cast<const double2*>(Xd + bi * LB * TLD + (i & 31) * TLD + (c & 31));
-        } else {
-            x = *reinterpret_cast<const double2*>(GPP_XOFF(bi, bc) + (i & 31) * LLD + (c & 31));
-        }
-        *reinterpret_cast<double2*>(Mb + (long long)i * ld + c) = x;
-    }
     }
 #undef GPP_XOFF
     GPP_STAMP(13)
@@ -743,33 +452,14 @@ leaf_potrf_trinv_v2_kernel(double* A, int ld, int kb, double* M, double* logdet_
 
 inline cudaError_t chol_set_attributes() {
     cudaError_t e = cudaFuncSetAttribute(leaf_potrf_trinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         LEAF_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(leaf_potrf_trinv_v2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             LEAF2_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(leaf_potrf_trinv_v2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             LEAF2_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(leaf_potrf_trinv_v2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             LEAF2_SMEM_BYTES);
+                                         LEAF2_SMEM_BYTES);
     if (e != cudaSuccess) return e;
     return gemm_set_attributes();
 }
 
-// leaf generation used by the drivers below (1 = first kernel, 2 / 3 = leaf_potrf_trinv_v2_kernel<2 / 3>)
-inline int g_leaf_version = 4;
-
 inline cudaError_t launch_leaf(double* A, int ld, int col, double* M, double* logdet_part, int* info, cudaStream_t st,
                                long long* prof = nullptr) {
-    if (g_leaf_version >= 4)
-        leaf_potrf_trinv_v2_kernel<4><<<1, LEAF_THREADS, LEAF2_SMEM_BYTES, st>>>(A, ld, col, M, logdet_part, info, prof);
-    else if (g_leaf_version == 3)
-        leaf_potrf_trinv_v2_kernel<3><<<1, LEAF_THREADS, LEAF2_SMEM_BYTES, st>>>(A, ld, col, M, logdet_part, info, prof);
-    else if (g_leaf_version == 2)
-        leaf_potrf_trinv_v2_kernel<2><<<1, LEAF_THREADS, LEAF2_SMEM_BYTES, st>>>(A, ld, col, M, logdet_part, info, prof);
-    else
-        leaf_potrf_trinv_kernel<<<1, LEAF_THREADS, LEAF_SMEM_BYTES, st>>>(A, ld, col, M, logdet_part, info);
+    leaf_potrf_trinv_kernel<<<1, LEAF_THREADS, LEAF2_SMEM_BYTES, st>>>(A, ld, col, M, logdet_part, info, prof);
     count_launch();
     return cudaGetLastError();
 }
@@ -975,8 +665,8 @@ inline cudaError_t trailing_update(double* A, int ld, int T, int p0, int pend, i
 inline cudaError_t panel_factor(double* A, double* M, int ld, int T, int p0, int pend, double* logdet_part, int* info,
                                 cudaStream_t st) {
     const int w = pend - p0;
-    if (w <= g_panel_base) return panel_factor_base(A, M, ld, T, p0, pend, logdet_part, info, st);
-    int half = g_panel_base;
+    if (w <= PANEL_BASE) return panel_factor_base(A, M, ld, T, p0, pend, logdet_part, info, st);
+    int half = PANEL_BASE;
     while (half * 2 < w) half *= 2;
     const int mid = p0 + half;
     GPP_TRY(panel_factor(A, M, ld, T, p0, mid, logdet_part, info, st));
@@ -986,8 +676,6 @@ inline cudaError_t panel_factor(double* A, double* M, int ld, int T, int p0, int
 
 inline int g_lookahead_depth = 2;  // 1: the next panel waits for the whole previous trailing update; 2: see below
 
-inline int g_tu_max_ctas = 0;       // cap on the CTAs of the bulk trailing update (0 = none): leaves SMs to the panel chain
-inline int g_inv_max_ctas = 0;      // cap on the CTAs of the overlapped inverse GEMMs
 inline int g_overlap_inverse = 1;   // start the early part of L^-1 (trtri_early) as soon as its columns of L are final
 
 // defined below; X is the scratch of the triangular inverse (may be null: no overlap)
@@ -1035,9 +723,9 @@ inline cudaError_t potrf_lookahead(double* A, double* M, int ld, int T, double* 
                 const int n2end = (nend + PB < T) ? nend + PB : T;
                 GPP_TRY(trailing_update(A, ld, T, p0, pend, nend, n2end, st));  // U(p,p+2)
                 GPP_TRY(cudaEventRecord(la.ev_tu[p], st));
-                GPP_TRY(trailing_update(A, ld, T, p0, pend, n2end, T, st, g_tu_max_ctas));  // U(p,p+3..)
+                GPP_TRY(trailing_update(A, ld, T, p0, pend, n2end, T, st));  // U(p,p+3..)
             } else {
-                GPP_TRY(trailing_update(A, ld, T, p0, pend, nend, T, st, g_tu_max_ctas));
+                GPP_TRY(trailing_update(A, ld, T, p0, pend, nend, T, st));
                 GPP_TRY(cudaEventRecord(la.ev_tu[p], st));
             }
             last_ev = p;
@@ -1133,16 +821,15 @@ inline cudaError_t trtri_early(const double* L, double* M, double* X, int ld, in
     const int H = trtri_split_point(T);
     if (H == 0) return cudaSuccess;
     for (int hb = 1; hb < H; hb *= 2)
-        GPP_TRY(trtri_level(L, M, X, ld, T, hb, 0, H / (2 * hb), 3, st, g_inv_max_ctas));
-    if (g_overlap_inverse == 2) return cudaSuccess;  // experiment: leave X21 to the late part
-    return trtri_level(L, M, X, ld, T, H, 0, 1, 1, st, g_inv_max_ctas);
+        GPP_TRY(trtri_level(L, M, X, ld, T, hb, 0, H / (2 * hb), 3, st));
+    return trtri_level(L, M, X, ld, T, H, 0, 1, 1, st);
 }
 inline cudaError_t trtri_late(const double* L, double* M, double* X, int ld, int T, cudaStream_t st) {
     const int H = trtri_split_point(T);
     if (H == 0) return cudaSuccess;
     for (int hb = 1; hb < H; hb *= 2)
         GPP_TRY(trtri_level(L, M, X, ld, T, hb, H / (2 * hb), (T + 2 * hb - 1) / (2 * hb), 3, st));
-    return trtri_level(L, M, X, ld, T, H, 0, 1, g_overlap_inverse == 2 ? 3 : 2, st);
+    return trtri_level(L, M, X, ld, T, H, 0, 1, 2, st);
 }
 
 // Kinv = M^T M (full symmetric storage); M lower: k-blocks [ti, T)

@@ -224,11 +224,8 @@ extern "C" int gpp_create(const gpp_problem* p, int device, gpp_handle** out) {
         // development switches (defaults are the production configuration)
         const char* e;
         if ((e = getenv("GPP_CHOL")) != nullptr) h->use_lookahead = strcmp(e, "blocked") != 0;
-        if ((e = getenv("GPP_LEAF")) != nullptr) g_leaf_version = std::max(1, std::min(4, atoi(e)));
         if ((e = getenv("GPP_PANEL")) != nullptr) g_panel_blocks = atoi(e);
         if ((e = getenv("GPP_OVERLAP_INV")) != nullptr) g_overlap_inverse = atoi(e);
-        if ((e = getenv("GPP_TU_CTAS")) != nullptr) g_tu_max_ctas = atoi(e);
-        if ((e = getenv("GPP_INV_CTAS")) != nullptr) g_inv_max_ctas = atoi(e);
         if ((e = getenv("GPP_GEMM_BM")) != nullptr) g_gemm_bm = atoi(e) == 64 ? 64 : 128;
         h->use_graph = h->T <= 16;  // N <= 2048: an evaluation is a chain of ~25-100 tiny launches
         if ((e = getenv("GPP_GRAPH")) != nullptr) h->use_graph = atoi(e) != 0;

@@ -212,54 +212,59 @@ static void leaf_lab(cudaStream_t st) {
     CHECK(cudaMalloc(&prof, 16 * 8));
     fill_kms<<<(128 * 128 + 255) / 256, 256, 0, st>>>(A0, ld, 128, 0.9, 0.1);
     Timer tm;
-    std::vector<double> Lref(128 * 128), Mref(128 * 128), Lh(128 * 128), Mh(128 * 128);
-    double ldref = 0;
-    for (int ver = 1; ver <= 4; ver++) {
-        g_leaf_version = ver;
-        float best = 1e9f, sum = 0;
-        for (int it = 0; it < 12; it++) {
-            CHECK(cudaMemcpyAsync(A, A0, 128 * 128 * 8, cudaMemcpyDeviceToDevice, st));
-            CHECK(cudaMemsetAsync(M, 0, 128 * 128 * 8, st));
-            CHECK(cudaMemsetAsync(prof, 0, 16 * 8, st));
-            tm.start(st);
-            CHECK(launch_leaf(A, ld, 0, M, ldp, info, st, ver >= 2 ? prof : nullptr));
-            float ms = tm.stop(st);
-            if (it >= 2) { best = fminf(best, ms); sum += ms; }
-        }
+    std::vector<double> Lref(128 * 128, 0.0), Lh(128 * 128), Mh(128 * 128);
+    {   // textbook Cholesky on the host as the reference factor
         CHECK(cudaStreamSynchronize(st));
-        int hinfo;
-        double hld;
-        CHECK(cudaMemcpy(&hinfo, info, 4, cudaMemcpyDeviceToHost));
-        CHECK(cudaMemcpy(&hld, ldp, 8, cudaMemcpyDeviceToHost));
-        CHECK(cudaMemcpy(Lh.data(), A, 128 * 128 * 8, cudaMemcpyDeviceToHost));
-        CHECK(cudaMemcpy(Mh.data(), M, 128 * 128 * 8, cudaMemcpyDeviceToHost));
-        inv_check<<<1, 128, 0, st>>>(A, M, ld, 1, mx);
-        CHECK(cudaStreamSynchronize(st));
-        double invres = read_max(mx);
-        printf("leaf v%d: best %.1f us  avg %.1f us  info %d  logdet_part %.15g  |M L - I|max %.3e\n", ver, best * 1e3,
-               sum / 10 * 1e3, hinfo, hld, invres);
-        if (ver == 1) { Lref = Lh; Mref = Mh; ldref = hld; }
-        else {
-            double dl = 0, dm = 0;
-            for (int i = 0; i < 128; i++)
-                for (int j = 0; j <= i; j++) {
-                    dl = fmax(dl, fabs(Lh[i * 128 + j] - Lref[i * 128 + j]));
-                    dm = fmax(dm, fabs(Mh[i * 128 + j] - Mref[i * 128 + j]));
-                }
-            double du = 0;
-            for (int i = 0; i < 128; i++)
-                for (int j = i + 1; j < 128; j++) du = fmax(du, fabs(Mh[i * 128 + j]));
-            printf("   vs v1: |dL|max %.3e |dM|max %.3e |M upper|max %.3e dlogdet %.3e\n", dl, dm, du, hld - ldref);
-            long long hp[16];
-            CHECK(cudaMemcpy(hp, prof, sizeof(hp), cudaMemcpyDeviceToHost));
-            const char* names[16] = {"start", "loaded", "potrf0", "trsm0", "syrk0", "potrf1", "trsm1", "syrk1", "potrf2",
-                                     "trsm2", "syrk2", "potrf3", "asm_done", "stored", "fact_done", "inv_warp_done"};
-            printf("   stamps (cycles since start):");
-            for (int i = 1; i < 16; i++) printf(" %s=%lld", names[i], hp[i] - hp[0]);
-            printf("\n");
+        CHECK(cudaMemcpy(Lref.data(), A0, 128 * 128 * 8, cudaMemcpyDeviceToHost));
+        for (int j = 0; j < 128; j++) {
+            double d = Lref[j * 128 + j];
+            for (int k = 0; k < j; k++) d -= Lref[j * 128 + k] * Lref[j * 128 + k];
+            d = sqrt(d);
+            Lref[j * 128 + j] = d;
+            for (int i = j + 1; i < 128; i++) {
+                double v = Lref[i * 128 + j];
+                for (int k = 0; k < j; k++) v -= Lref[i * 128 + k] * Lref[j * 128 + k];
+                Lref[i * 128 + j] = v / d;
+            }
         }
     }
-    g_leaf_version = 2;
+    double ldref = 0.0;
+    for (int j = 0; j < 128; j++) ldref += log(Lref[j * 128 + j]);
+    float best = 1e9f, sum = 0;
+    for (int it = 0; it < 12; it++) {
+        CHECK(cudaMemcpyAsync(A, A0, 128 * 128 * 8, cudaMemcpyDeviceToDevice, st));
+        CHECK(cudaMemsetAsync(M, 0, 128 * 128 * 8, st));
+        CHECK(cudaMemsetAsync(prof, 0, 16 * 8, st));
+        tm.start(st);
+        CHECK(launch_leaf(A, ld, 0, M, ldp, info, st, prof));
+        float ms = tm.stop(st);
+        if (it >= 2) { best = fminf(best, ms); sum += ms; }
+    }
+    CHECK(cudaStreamSynchronize(st));
+    int hinfo;
+    double hld;
+    CHECK(cudaMemcpy(&hinfo, info, 4, cudaMemcpyDeviceToHost));
+    CHECK(cudaMemcpy(&hld, ldp, 8, cudaMemcpyDeviceToHost));
+    CHECK(cudaMemcpy(Lh.data(), A, 128 * 128 * 8, cudaMemcpyDeviceToHost));
+    CHECK(cudaMemcpy(Mh.data(), M, 128 * 128 * 8, cudaMemcpyDeviceToHost));
+    inv_check<<<1, 128, 0, st>>>(A, M, ld, 1, mx);
+    CHECK(cudaStreamSynchronize(st));
+    double invres = read_max(mx);
+    double dl = 0, du = 0;
+    for (int i = 0; i < 128; i++)
+        for (int j = 0; j < 128; j++) {
+            if (j <= i) dl = fmax(dl, fabs(Lh[i * 128 + j] - Lref[i * 128 + j]));
+            else du = fmax(du, fabs(Mh[i * 128 + j]));
+        }
+    printf("leaf: best %.1f us  avg %.1f us  info %d  |L - host chol|max %.3e  dlogdet %.3e  |M L - I|max %.3e  "
+           "|M upper|max %.3e\n", best * 1e3, sum / 10 * 1e3, hinfo, dl, hld - ldref, invres, du);
+    long long hp[16];
+    CHECK(cudaMemcpy(hp, prof, sizeof(hp), cudaMemcpyDeviceToHost));
+    const char* names[16] = {"start", "loaded", "potrf0", "trsm0", "syrk0", "potrf1", "trsm1", "syrk1", "potrf2",
+                             "trsm2", "syrk2", "potrf3", "asm_done", "stored", "fact_done", "inv_warp_done"};
+    printf("   stamps (cycles since start):");
+    for (int i = 1; i < 16; i++) printf(" %s=%lld", names[i], hp[i] - hp[0]);
+    printf("\n");
     cudaFree(A0); cudaFree(A); cudaFree(M); cudaFree(ldp); cudaFree(mx); cudaFree(info); cudaFree(prof);
 }
 
@@ -334,17 +339,15 @@ static void potrf_lab(int n, cudaStream_t st) {
     CholLookahead la;
     CHECK(la.init(T));
     Timer tm;
-    struct Var { const char* name; int leaf, bm, look, pb, depth, base; };
-    const Var vars[] = {{"blocked  leaf4 P4          ", 4, 64, 0, 4, 1, 4}, {"look d1 leaf4 P8 base4    ", 4, 64, 1, 8, 1, 4},
-                        {"look d1 leaf4 P8 base2    ", 4, 64, 1, 8, 1, 2}, {"look d2 leaf4 P8 base2    ", 4, 64, 1, 8, 2, 2},
-                        {"look d2 leaf4 P4 base2    ", 4, 64, 1, 4, 2, 2}};
+    struct Var { const char* name; int bm, look, pb, depth; };
+    const Var vars[] = {{"blocked   P4        ", 64, 0, 4, 1}, {"lookahead P8 depth 1", 64, 1, 8, 1},
+                        {"lookahead P8 depth 2", 64, 1, 8, 2}, {"lookahead P4 depth 2", 64, 1, 4, 2},
+                        {"lookahead P8 bm128  ", 128, 1, 8, 2}};
     const int nblk = (int)((ld * ld + 255) / 256);
     for (int v = 0; v < 5; v++) {
-        g_leaf_version = vars[v].leaf;
         g_gemm_bm = vars[v].bm;
         g_panel_blocks = vars[v].pb;
         g_lookahead_depth = vars[v].depth;
-        g_panel_base = vars[v].base;
         float best = 1e9f;
         for (int it = 0; it < 3; it++) {
             CHECK(cudaMemcpyAsync(A, A0, (size_t)ld * ld * 8, cudaMemcpyDeviceToDevice, st));
@@ -377,11 +380,9 @@ static void potrf_lab(int n, cudaStream_t st) {
                n, vars[v].name, best, (double)n * n * n / 3.0 / (best * 1e-3) / 1e12, hinfo, logdet, res, invres, dl);
         fflush(stdout);
     }
-    g_leaf_version = 2;
     g_gemm_bm = 64;
     g_panel_blocks = 0;
     g_lookahead_depth = 2;
-    g_panel_base = 2;
     la.destroy();
     cudaFree(A0); cudaFree(A); cudaFree(M); cudaFree(Lref); cudaFree(ldp); cudaFree(mx); cudaFree(info);
 }
