@@ -357,9 +357,17 @@ class _StubEngine:
         return out
 
 
-def self_check(likobj, fast: FastObjective, trials: int = 2, tol: float = 1e-9) -> bool:
-    """Compare ``fast.fun`` with the torch path ``likobj.fun`` through a stub engine on random theta."""
+def self_check(likobj, fast: FastObjective, trials: int = 2, tol: Optional[float] = None) -> bool:
+    """Compare ``fast.fun`` with the torch path ``likobj.fun`` through a stub engine on random theta.
+
+    The closed forms are evaluated in float64.  For a model whose parameters are float32 (the reference's default
+    ``dtype=torch.float``) the torch path rounds every transform and prior term to float32 -- e.g. ``lb + exp(raw)``
+    loses the 1e-8 noise floor and the horseshoe prior's gradient moves by ~1e-4 relative -- so there the check
+    only guards the structure (1e-3); float64 models are held to 1e-9."""
     model = likobj.model
+    if tol is None:
+        is32 = any(p.dtype == torch.float32 for p in model.parameters())
+        tol = 1e-3 if is32 else 1e-9
     table = model._latent_table()
     n_mean, _ = model._mean_layout()
     stub = _StubEngine(len(model._quant_columns()), 0 if table is None else int(table.shape[1]),

@@ -194,6 +194,11 @@ def _fit_model_from_state(likobj, theta0, jac, options, method="trust-constr", c
     except Exception as e:
         if isinstance(e, (NotPSDError, NanError)):
             return e  # unstable starting point: scored as +inf by the caller
+        if isinstance(e, ValueError) and "within the support" in str(e):
+            # torch path only: a float32 softplus underflowed to 0 and torch.distributions rejected the LogNormal
+            # prior's argument.  The reference aborts the whole multi-start fit here; one runaway restart is
+            # scored +inf instead.
+            return NanError(str(e))
         raise
 
 

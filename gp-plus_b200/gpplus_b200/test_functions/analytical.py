@@ -82,3 +82,17 @@ def borehole_mixed_variables(n=100, X=None, qual_dict={0: 5, 6: 3}, noise_std=0.
     if noise_std > 0.0:
         y = y + np.random.randn(*y.shape) * noise_std
     return (X, y) if generated else y
+
+
+def sine_1D(n=100, X=None, noise_std=0.0, frequency=1.0, absolute_value_flag=False, random_state=None, shuffle=True):
+    """y = sin(2 pi f x) on [-1, 1] (test_functions/analytical.py:224-255 of the reference, Example 05)."""
+    if random_state is not None:
+        np.random.seed(random_state)
+    generated = X is None
+    if generated:
+        X = _sobol_design(n, ([-1.0], [1.0]), random_state)
+    X = np.asarray(X)
+    y = np.sin(2 * np.pi * frequency * X[:, 0])
+    if absolute_value_flag:
+        y = np.abs(y)
+    return _finish(X, y, generated, noise_std, shuffle)

@@ -314,3 +314,20 @@ def test_host_objective_falls_back_for_unsupported_models():
     m2 = GP_Plus(torch.tensor(X), torch.tensor(y), qual_dict={2: 3}, dtype=torch.float64)
     assert FO.build(m2, True, [0.1, 0]) is None         # weight regularisation: torch path only
     assert FO.build(m2, False, [0, 0]) is not None
+
+
+def test_float32_models_take_the_closed_form_path():
+    """Default-dtype (float32) models: the closed forms run in float64, the torch path in float32; they agree to
+    float32 accuracy and the fit does not fall back to the 1.4 ms torch objective."""
+    from gpplus_b200.models import GP_Plus
+    from gpplus_b200.optim import _fast_objective as FO
+    from gpplus_b200.optim.mll_scipy import MLLObjective
+    rng = np.random.default_rng(0)
+    X = np.hstack([rng.standard_normal((50, 3)), rng.integers(0, 3, (50, 1)).astype(float)])
+    y = np.sin(X[:, 0]) + 0.2 * X[:, 3]
+    m = GP_Plus(torch.tensor(X), torch.tensor(y), qual_dict={3: 3})
+    assert next(m.parameters()).dtype == torch.float32
+    obj = MLLObjective(m, True, [0, 0])
+    fast = FO.build(m, True, [0, 0])
+    assert fast is not None and FO.self_check(obj, fast, trials=4)
+    assert not FO.self_check(obj, fast, trials=4, tol=1e-9)   # float32 rounding of the torch path is visible
