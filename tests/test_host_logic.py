@@ -331,3 +331,4 @@ def test_float32_models_take_the_closed_form_path():
     fast = FO.build(m, True, [0, 0])
     assert fast is not None and FO.self_check(obj, fast, trials=4)
     assert not FO.self_check(obj, fast, trials=4, tol=1e-9)   # float32 rounding of the torch path is visible
+
