@@ -4,7 +4,7 @@ sys.path.insert(0, '.'); sys.path.insert(0, 'gp-plus_b200'); sys.path.insert(0, 
 import numpy as np
 from gpplus_b200 import _engine as E
 from problems import engine_kwargs, make_candidates, make_hyper, make_problem
-for n, dz in ((200, 2), (700, 0)):
+for n, dz in ((200, 2), (700, 0), (1100, 2)):
     p = make_problem(n, 5, 2, dz=dz, n_combo=5 if dz else 0, n_noise=2, seed=3)
     h = make_hyper(p, seed=4)
     eng = E.Engine(**engine_kwargs(p))
