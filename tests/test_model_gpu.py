@@ -263,3 +263,34 @@ def test_sobol_indices_of_an_additive_function():
     assert abs(S.sum() - 1.0) < 0.05 and np.all(np.abs(S - ST) < 0.05)
     assert abs(S[0, 2]) < 0.02            # x2 is inert
     assert S[0, 0] > S[0, 1] > 0.0        # var(2 x0) = 4/3 > var(x1^2) = 4/45
+
+
+@pytest.mark.parametrize("maker", [_c3, lambda: _c2("Matern52Kernel")])
+def test_device_side_table_preparation_equals_host_preparation(maker):
+    """prepare_candidate_table_on_device (ordering, gather and level ranking as torch device ops) must hand the
+    engine exactly the arrays of the host preparation, including the per-slice setlevels quirk."""
+    from gpplus_b200.bayesian_optimizations import (prepare_candidate_table, prepare_candidate_table_on_device,
+                                                    score_prepared)
+    m, spec, Xte, yte = maker()
+    rng = np.random.default_rng(5)
+    M = 5000
+    xtr = m.train_inputs[0].double().numpy()
+    table = xtr[rng.integers(0, xtr.shape[0], M)].copy()
+    qcols = m._quant_columns()
+    table[:, qcols] += 0.1 * rng.standard_normal((M, len(qcols)))
+    n_src = 4
+    if spec.get("m_gp") != "multiple_constant":   # mixed-variable model: last column is a 5-level categorical
+        table[:, -1] = rng.integers(0, n_src, M)
+    host = prepare_candidate_table(m, table, n_src)
+    dev = prepare_candidate_table_on_device(m, table, n_src, 0)
+    assert np.array_equal(host["order"], dev["order"]) and host["lo"] == dev["lo"] and host["count"] == dev["count"]
+    assert np.array_equal(host["xq"], dev["xq"].cpu().numpy())
+    assert np.array_equal(host["cost_idx"], dev["cost_idx"].cpu().numpy())
+    for key in ("level_idx", "mean_idx"):
+        assert (host[key] is None) == (dev[key] is None)
+        if host[key] is not None:
+            assert np.array_equal(host[key], dev[key].cpu().numpy())
+    best, costs = [0.3, 0.2, 0.1, 0.0], [1000.0, 100.0, 10.0, 100.0]
+    a = score_prepared(m, host, best, costs, maximize=False, return_scores=True)
+    b = score_prepared(m, dev, best, costs, maximize=False, return_scores=True)
+    assert a[0] == b[0] and a[1] == b[1] and np.array_equal(a[2], b[2])
