@@ -1,5 +1,6 @@
-"""Seed python / numpy / torch RNGs (utils/set_seed.py:6-15): restart starting points are drawn from
-the global torch RNG, so this fixes the multi-start list."""
+"""One seed for every RNG the fit touches.  Restart starting points are drawn from torch's global generator
+(optim/mll_scipy._sample_from_prior), data generators use numpy's, so both must be fixed for a reproducible
+multi-start list (reference: utils/set_seed.py)."""
 import random
 
 import numpy as np
@@ -7,8 +8,7 @@ import torch
 
 
 def set_seed(seed):
-    random.seed(seed)
-    torch.manual_seed(seed)
-    np.random.seed(seed)
+    for seeder in (random.seed, np.random.seed, torch.manual_seed):
+        seeder(seed)
     if torch.cuda.is_available():
         torch.cuda.manual_seed_all(seed)
