@@ -1,0 +1,37 @@
+"""bench.py's output contract, checked on the arm that runs without a GPU (the CPU reference arm)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_one_contract_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--n", "256", "--steps",
+                          "1", "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "evals/s" and d["higher_is_better"] is True
+    assert d["metric"] == "MLL+grad evals/sec (N=16k, fp64)" and d["dtype"] == "f64" and d["vs_baseline"] is None
+    assert d["value"] > 0 and d["config"]["workload"].startswith("synthetic exact GP N=256")
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_is_silent_on_other_ranks():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--n",
+                          "256"], capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_our_arm_fails_loudly_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        return
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True,
+                         timeout=300, cwd=ROOT)
+    assert out.returncode != 0 and "no CUDA device" in (out.stderr + out.stdout)
