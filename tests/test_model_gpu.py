@@ -50,7 +50,8 @@ def _c3():
     return m, spec, Xte, yte
 
 
-@pytest.mark.parametrize("maker", [_c1, _c2, lambda: _c2("Matern52Kernel"), _c3])
+@pytest.mark.parametrize("maker", [_c1, _c2, lambda: _c2("Matern52Kernel"), lambda: _c2("Matern32Kernel"),
+                                   lambda: _c2("RBFKernel"), _c3])
 def test_objective_matches_oracle(maker):
     from gpplus_b200.optim.mll_scipy import MLLObjective, _sample_from_prior
     from oracle import gpplus_oracle as GO
@@ -294,3 +295,33 @@ def test_device_side_table_preparation_equals_host_preparation(maker):
     a = score_prepared(m, host, best, costs, maximize=False, return_scores=True)
     b = score_prepared(m, dev, best, costs, maximize=False, return_scores=True)
     assert a[0] == b[0] and a[1] == b[1] and np.array_equal(a[2], b[2])
+
+
+def test_plain_gpr_with_string_kernels():
+    """GPR (models/gpregression.py:38-175) built from a kernel name: likelihood against the natural-parameter oracle,
+    prediction interpolates a smooth function."""
+    from gpplus_b200.models import GPR
+    from oracle import gp_oracle as O
+    rng = np.random.default_rng(8)
+    n = 150
+    X = rng.uniform(-1, 1, (n, 3))
+    y = np.sin(2 * X[:, 0]) + X[:, 1] ** 2 - 0.5 * X[:, 2]
+    for name, kind, wfun in (("RBFKernel", 0, lambda ls: 0.5 / ls ** 2), ("Matern52Kernel", 2, lambda ls: 1.0 / ls ** 2)):
+        m = GPR(torch.tensor(X), torch.tensor(y), name, noise_indices=[], lb_noise=1e-8)
+        m = m.double() if hasattr(m, "double") else m
+        with torch.no_grad():
+            m.covar_module.base_kernel.raw_lengthscale.fill_(0.3)
+            m.likelihood.noise_covar.raw_noise.fill_(-7.0)
+        lm = float(m.log_marginal().detach())
+        ls = float(np.exp(0.3))
+        ys = (y - y.min()) / (y.max() - y.min())
+        p = {"n": n, "dq": 3, "dz": 0, "n_combo": 0, "n_noise": 1, "n_mean": 0, "kernel": kind, "xq": X, "y": ys,
+             "level_idx": None, "noise_idx": None, "mean_idx": None}
+        h = {"w": np.full(3, wfun(ls)), "z": None, "sigma_f2": float(m.covar_module.outputscale),
+             "noise": np.array([1e-8 + np.exp(-7.0)]), "beta": None}
+        ref = O.mll(p, h, want_grad=False)
+        assert abs(-lm - ref["nll"]) <= 1e-8 * abs(ref["nll"])
+        Xs = rng.uniform(-1, 1, (50, 3))
+        mu, sd = m.predict(torch.tensor(Xs), return_std=True)
+        truth = np.sin(2 * Xs[:, 0]) + Xs[:, 1] ** 2 - 0.5 * Xs[:, 2]
+        assert float(np.sqrt(np.mean((mu.numpy() - truth) ** 2))) < 0.15 and bool(torch.all(sd > 0))
