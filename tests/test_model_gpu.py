@@ -325,3 +325,29 @@ def test_plain_gpr_with_string_kernels():
         mu, sd = m.predict(torch.tensor(Xs), return_std=True)
         truth = np.sin(2 * Xs[:, 0]) + Xs[:, 1] ** 2 - 0.5 * Xs[:, 2]
         assert float(np.sqrt(np.mean((mu.numpy() - truth) ** 2))) < 0.15 and bool(torch.all(sd > 0))
+
+
+@pytest.mark.parametrize("kwargs", [dict(fix_noise=True, fix_noise_val=1e-4), dict(m_gp="single_zero"),
+                                    dict(fixed_length_scale=True, fixed_length_scale_val=torch.tensor([[0.5, 0.5, 0.5]])),
+                                    dict(lb_noise=1e-6, quant_correlation_class="Matern32Kernel")])
+def test_constructor_variants_fit_through_the_native_objective(kwargs):
+    """Frozen noise / zero mean / frozen lengthscales / other noise floor: the layout handed to gpp_objective has
+    frozen blocks (negative offsets); value and gradient must still equal the torch path, and a fit must run."""
+    from gpplus_b200.models import GP_Plus
+    from gpplus_b200.optim.mll_scipy import MLLObjective, fit_model_scipy
+    rng = np.random.default_rng(4)
+    X = rng.uniform(-1, 1, (120, 3))
+    y = np.sin(2 * X[:, 0]) + X[:, 1] ** 2 - 0.5 * X[:, 2] + 0.01 * rng.standard_normal(120)
+    m = GP_Plus(torch.tensor(X), torch.tensor(y), dtype=torch.float64, **kwargs)
+    obj = MLLObjective(m, True, [0, 0])
+    assert obj.enable_fast_path()
+    th = obj.pack_parameters() + 0.1 * rng.standard_normal(obj.pack_parameters().shape[0])
+    f_ref, g_ref = obj.fun(th)
+    f, g = obj.fun_fast(th)
+    assert abs(f - f_ref) <= 1e-10 * max(1.0, abs(f_ref)) and np.max(np.abs(g - g_ref)) <= 1e-9 * max(1.0, np.max(np.abs(g_ref)))
+    torch.manual_seed(0)
+    res, best = fit_model_scipy(m, num_restarts=7, bounds=True)
+    assert np.isfinite(best) and len(res) == 8 and best == min(r.fun for r in res if not isinstance(r, Exception))
+    mu, sd = m.predict(torch.tensor(X), return_std=True)
+    assert bool(torch.all(torch.isfinite(mu))) and bool(torch.all(sd > 0))
+    assert float(torch.sqrt(torch.mean((mu - torch.tensor(y)) ** 2))) < 0.35   # y spans about +-1.5
