@@ -218,10 +218,14 @@ def _workers_per_gpu(n_train: int) -> int:
     env = os.environ.get("GPPLUS_WORKERS_PER_GPU")
     if env:
         return max(1, int(env))
-    # small problems are launch-latency bound: keep several restarts in flight per GPU
+    # small and mid-size problems leave most SMs idle in the latency-bound parts of an evaluation (leaf chain, small
+    # GEMMs): keep several restarts in flight per GPU.  Measured evals/s at 1 -> 2 -> 4 workers: n=1536 0.8k -> 1.3k ->
+    # 1.8k, n=3072 325 -> 537, n=6144 96 -> 120; at n=500 eight workers sustain 8-9k.
     if n_train <= 1024:
         return 8
-    if n_train <= 4096:
+    if n_train <= 2048:
+        return 4
+    if n_train <= 8192:
         return 2
     return 1
 
