@@ -531,6 +531,58 @@ class GP_Plus(GPR):
             eng.close()
 
 
+    def score(self, Xtest, ytest, plot_MSE=True, title=None, seperate_levels=False):
+        """MSE of the predictive mean and the estimated noise, printed as the reference does (gp_plus.py:634-666).
+        The parity plot is drawn only when matplotlib is installed."""
+        Xtest = data_type_check(Xtest)
+        ytest = data_type_check(ytest).reshape(-1)
+        ypred = self.predict(Xtest, return_std=False)
+        mse = ((ytest - ypred) ** 2).mean()
+        noise = self.noise_value()
+        print("################MSE######################")
+        print(f"MSE = {mse:.5f}")
+        print("################Noise####################")
+        print(f"The estimated noise parameter (varaince) is {noise}")
+        print(f"The estimated noise std is {np.sqrt(noise.cpu())}")
+        print("#########################################")
+        if plot_MSE:
+            try:
+                import matplotlib.pyplot as plt
+            except ImportError:
+                plt = None
+            if plt is not None:
+                plt.figure(figsize=(8, 6))
+                plt.plot(ytest.numpy(), ypred.numpy(), "ro", label="Data")
+                plt.plot(ytest.numpy(), ytest.numpy(), "b", label="MSE = " + str(np.round(float(mse), 3)))
+                plt.xlabel(r"Y_True")
+                plt.ylabel(r"Y_predict")
+                plt.legend()
+                if title is not None:
+                    plt.title(title)
+        if seperate_levels and len(self._qual_cols) > 0:
+            for level in range(self.num_levels_per_var[0]):
+                rows = torch.where(Xtest[:, self._qual_cols[0]] == level)[0]
+                self.score(Xtest[rows, ...], ytest[rows], plot_MSE=plot_MSE,
+                           title="results Only Source " + str(level), seperate_levels=False)
+        return ypred
+
+    def get_params(self, name=None):
+        """Raw parameters by their state-dict names, or one of 'Mean' / 'Sigma' / 'Noise' / 'Omega'
+        (gp_plus.py:962-982)."""
+        params = {n: value for n, value in self.named_parameters()}
+        print("###################Parameters###########################")
+        if name is None:
+            print(params)
+            return params
+        key = {"Mean": "mean_module.constant", "Sigma": "covar_module.raw_outputscale",
+               "Noise": "likelihood.noise_covar.raw_noise"}.get(name)
+        if name == "Omega":
+            key = [n for n, v in params.items() if "raw_lengthscale" in n and v.numel() > 1][-1]
+        if key is None:
+            raise KeyError(name)
+        print(params[key])
+        return params[key]
+
     def get_latent_space(self):
         if len(self.qual_kernel_columns) == 0:
             raise RuntimeError("No categorical Variable, No latent positions")

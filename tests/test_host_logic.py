@@ -332,3 +332,15 @@ def test_float32_models_take_the_closed_form_path():
     assert fast is not None and FO.self_check(obj, fast, trials=4)
     assert not FO.self_check(obj, fast, trials=4, tol=1e-9)   # float32 rounding of the torch path is visible
 
+
+
+def test_get_params_names():
+    from gpplus_b200.models import GP_Plus
+    rng = np.random.default_rng(0)
+    X = np.hstack([rng.standard_normal((30, 3)), rng.integers(0, 3, (30, 1)).astype(float)])
+    m = GP_Plus(torch.tensor(X), torch.tensor(X[:, 0]), qual_dict={3: 3}, dtype=torch.float64)
+    assert m.get_params("Omega").shape == (1, 3)
+    assert m.get_params("Sigma") is m.covar_module.raw_outputscale
+    assert m.get_params("Noise") is m.likelihood.noise_covar.raw_noise
+    assert m.get_params("Mean") is m.mean_module.constant
+    assert "latent[3]" in m.get_params()
