@@ -12,3 +12,5 @@ Xtrain, Xtest, ytrain, ytest = train_test_split_normalizeX(X, y, test_size=0.99)
 model = GP_Plus(Xtrain, ytrain, quant_correlation_class="Matern32Kernel")
 model.fit(n_jobs=-1, num_restarts=16)
 model.evaluation(Xtest, ytest)
+model.score(Xtest, ytest, plot_MSE=False)
+model.get_params('Omega')

@@ -577,7 +577,9 @@ class GP_Plus(GPR):
         key = {"Mean": "mean_module.constant", "Sigma": "covar_module.raw_outputscale",
                "Noise": "likelihood.noise_covar.raw_noise"}.get(name)
         if name == "Omega":
-            key = [n for n, v in params.items() if "raw_lengthscale" in n and v.numel() > 1][-1]
+            ls = [n for n, v in params.items() if "raw_lengthscale" in n]
+            ard = [n for n in ls if params[n].numel() > 1]  # the reference picks the ARD one; 1-D inputs have none
+            key = (ard or ls or [None])[-1]
         if key is None:
             raise KeyError(name)
         print(params[key])
