@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import threading
-from typing import Dict, Optional, Sequence
+from typing import Dict, Sequence
 
 import numpy as np
 

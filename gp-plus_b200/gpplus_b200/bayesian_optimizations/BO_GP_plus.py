@@ -20,7 +20,7 @@ Deviations from the reference source, which cannot run as published: it construc
 from __future__ import annotations
 
 import os
-from typing import Callable, Dict, List, Optional, Sequence, Tuple
+from typing import Dict, Optional, Sequence
 
 import numpy as np
 import torch

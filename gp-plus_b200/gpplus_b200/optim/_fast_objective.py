@@ -21,7 +21,7 @@ from typing import Callable, List, Optional, Tuple
 import numpy as np
 import torch
 
-from .._compat import ConstantMean, LogNormalPrior, NormalPrior, ZeroMean
+from .._compat import LogNormalPrior, NormalPrior
 from ..priors import LogHalfHorseshoePrior, MollifiedUniformPrior
 
 _LN10 = math.log(10.0)
