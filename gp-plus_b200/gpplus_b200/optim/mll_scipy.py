@@ -78,6 +78,7 @@ class MLLObjective:
         self.regularization_parameter = regularization_parameter
         self.param_shapes = OrderedDict()
         self._fast = None
+        self._native = True
         for n, p in self.model.named_parameters():
             if p.requires_grad:
                 self.param_shapes[n] = p.size() if len(p.size()) > 0 else torch.Size([1])
@@ -119,6 +120,8 @@ class MLLObjective:
         fast = FO.build(self.model, self.add_prior, self.regularization_parameter)
         if fast is not None and FO.self_check(self, fast):
             self._fast = fast
+        # the closed forms evaluated by numpy on the host (0) or inside the library by gpp_objective (default)
+        self._native = os.environ.get("GPPLUS_NATIVE_OBJECTIVE", "1") != "0"
         return self._fast is not None
 
     def fun_fast(self, x: np.ndarray, return_grad=True) -> Union[float, Tuple[float, np.ndarray]]:
@@ -126,7 +129,7 @@ class MLLObjective:
         model's parameters are NOT updated; ``fit_model_scipy`` loads the best theta at the end)."""
         eng = self.model._get_engine()
         self.model._factor_key = None
-        if os.environ.get("GPPLUS_NATIVE_OBJECTIVE", "1") != "0":
+        if self._native:
             if getattr(eng, "_layout_owner", None) is not self._fast:
                 eng.set_theta_layout(self._fast.layout_spec())
                 eng._layout_owner = self._fast
