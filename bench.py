@@ -29,38 +29,26 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "gp-plus_b200"))
 
-N_HEADLINE = 16384
-D = 10
+import bench_workloads as W  # noqa: E402
+
+N_HEADLINE = W.N_HEADLINE
+D = W.D
 LOG2PI = 1.8378770664093453
+GOLDEN = os.path.join(ROOT, "tests", "golden", "c4_n%d_matern52.json")
+
+METRIC = "MLL+grad evals/sec (N=16k, fp64)"
 
 
-# ------------------------------------------------------------------------------------------------
-def make_workload(n):
-    """Sobol(d=10, seed=0) scaled to the wing bounds, y = wing(X) + N(0, 0.5^2), X standardised
-    per column, y min-max scaled by the model."""
-    from scipy.stats.qmc import Sobol, scale
-    from gpplus_b200.test_functions.analytical import WING_BOUNDS, wing_weight
-    X = scale(Sobol(d=D, seed=0).random(n), l_bounds=WING_BOUNDS[0], u_bounds=WING_BOUNDS[1])
-    rng = np.random.RandomState(0)
-    y = wing_weight(X) + 0.5 * rng.randn(n)
-    Xs = (X - X.mean(0)) / X.std(0)
-    return Xs, y
+def bench_config(n):
+    """The ``config`` object of the JSON line -- byte-identical in both arms (ours / --impl reference)."""
+    return {"workload": "synthetic exact GP N=%d D=10 Matern-5/2 FP64 MLL+gradient (bench_workloads.c4_workload)" % n,
+            "points": "the 65 seeded prior draws of a 64-restart fit (torch.manual_seed(0); SURVEY 8(d)), cycled",
+            "l2": "inputs larger than L2: each step streams three %.1f GiB work matrices" % (8.0 * n * n / 2 ** 30)}
 
 
-def theta_points(model, count, seed=0):
-    """theta_init (all raw parameters 0) and small perturbations of it: well-conditioned, distinct every step."""
-    from gpplus_b200.optim.mll_scipy import MLLObjective
-    obj = MLLObjective(model, True, [0, 0])
-    base = obj.pack_parameters() * 0.0
-    rng = np.random.RandomState(seed)
-    return obj, [base + (0.05 * rng.randn(base.shape[0]) if k > 0 else 0.0) for k in range(count)]
-
-
-def natural_from_theta(theta):
-    """raw [noise, outputscale, omega_1..10, mean] -> natural parameters of the C ABI (Matern-5/2)."""
-    th = np.asarray(theta, dtype=np.float32).astype(np.float64)  # the reference casts theta to float32
-    return {"w": 2.0 * 10.0 ** th[2:12], "z": None, "sigma_f2": float(np.log1p(np.exp(th[1]))),
-            "noise": np.array([1e-8 + np.exp(th[0])]), "beta": th[12:13]}
+def step_theta(thetas, k, rank=0):
+    """theta of timed step k on ``rank``: prior draw 1 + (k + 8 rank) mod 65 (index 0 of ``thetas`` is theta_init)."""
+    return thetas[1 + (k + 8 * rank) % W.N_PRIOR_DRAWS]
 
 
 class ClockSampler:
@@ -130,63 +118,95 @@ def measure_fp64_peak(device):
     return 2.0 * 8192 ** 3 / (best * 1e-3) / 1e12
 
 
-def cpu_oracle_rate(n_sample, steps, warmup, n_target, threads=None):
-    """evals/s of the CPU oracle (the reference's torch path restated) at n_target, measured on a bounded
-    sample of the same workload (first n_sample points) and scaled by the O(N^3) cost."""
+def oracle_full_size(n, theta_list, threads=None, warm=True):
+    """Wall seconds of REAL oracle MLL+gradient evaluations at the full size ``n`` (no extrapolation): the CPU
+    restatement of the reference's torch path (oracle/gp_oracle.mll: dense float64 K, torch Cholesky, autograd), on
+    ``threads`` host threads.  Returns ([seconds per evaluation], [oracle results], threads used)."""
     import torch
     from oracle import gp_oracle as O
     if threads:
         torch.set_num_threads(threads)
-    X, y = make_workload(n_target)
-    X, y = X[:n_sample], y[:n_sample]
-    ys = (y - y.min()) / (y.max() - y.min())
-    p = {"n": n_sample, "dq": D, "dz": 0, "n_combo": 0, "n_noise": 1, "n_mean": 1, "kernel": O.KERNEL_MATERN52,
-         "xq": X, "y": ys, "level_idx": None, "noise_idx": None, "mean_idx": None}
-    rng = np.random.RandomState(1)
-    times = []
-    for k in range(warmup + steps):
-        h = natural_from_theta(0.05 * rng.randn(13))
+    if warm:  # page in torch / MKL before the clock starts
+        O.mll(W.c4_oracle_problem(1024), W.c4_natural(theta_list[0]), want_grad=True)
+    prob = W.c4_oracle_problem(n)
+    secs, outs = [], []
+    for th in theta_list:
         t0 = time.time()
-        O.mll(p, h, want_grad=True)
-        if k >= warmup:
-            times.append(time.time() - t0)
-    t = sum(times) / len(times)
-    return 1.0 / (t * (n_target / n_sample) ** 3), t, torch.get_num_threads()
+        outs.append(O.mll(prob, W.c4_natural(th), want_grad=True))
+        secs.append(time.time() - t0)
+    return secs, outs, torch.get_num_threads()
 
 
 # ------------------------------------------------------------------------------------------------
 def run_reference(args):
-    """The reference arm: the reference's own CPU torch path for this workload.  The reference cannot be
-    imported (gpytorch / botorch absent, no network), so the CPU restatement in oracle/ is timed (kind
-    "port"), with every host thread, on a bounded sample per step."""
+    """The reference arm: the reference's own CPU torch path for this workload.  The reference cannot be imported
+    on the GPU box (gpytorch / botorch are not installed anywhere, /root/reference does not travel), so the CPU
+    restatement in oracle/ -- pinned to the reference's own code by tests/test_reference_pin.py -- is timed (kind
+    "port") with every host thread, at the FULL size: ``steps`` in the line is the number of evaluations actually
+    run (bounded so that the arm ends within a few minutes; ``steps_requested`` keeps the driver's K)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_sample = min(args.n, 4096)
-    rate, t_step, threads = cpu_oracle_rate(n_sample, max(1, args.steps), max(0, min(args.warmup, 1)), args.n, cores)
+    thetas = W.c4_theta_points(W.c4_model(256))
+    budget_s = float(os.environ.get("GPPLUS_REF_BUDGET_S", "150"))
+    run = []
+    secs = []
+    t_begin = time.time()
+    for k in range(max(1, args.steps)):
+        s, _, threads = oracle_full_size(args.n, [step_theta(thetas, k)], cores, warm=(k == 0))
+        secs += s
+        run.append(k)
+        if time.time() - t_begin + max(secs) > budget_s:
+            break
+    steps_run = len(secs)
+    rate = steps_run / sum(secs)
     line = {
-        "impl": "reference", "metric": "MLL+grad evals/sec (N=16k, fp64)", "value": rate, "unit": "evals/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 / rate, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "evals/s",
+        "n_gpus": args.gpus, "steps": steps_run, "warmup": 0, "steps_requested": args.steps,
+        "warmup_requested": args.warmup,
+        "ms_per_step": 1e3 * sum(secs) / steps_run, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "synthetic exact GP N=%d D=10 Matern-5/2 FP64 MLL+gradient" % args.n,
-                   "l2": "inputs larger than L2 (K is %.1f GiB)" % (8.0 * args.n ** 2 / 2 ** 30)},
+        "config": bench_config(args.n),
         "cpu_baseline": {"value": rate, "unit": "evals/s", "cores": threads, "kind": "port",
-                         "sample": "one oracle MLL+grad eval per step on the first %d points of the workload "
-                                   "(%.2f s each), scaled by (N/%d)^3 to N=%d" % (n_sample, t_step, n_sample, args.n)},
+                         "sample": "%d real oracle MLL+grad evaluation(s) at the full N=%d on the first timed theta "
+                                   "points (%s s each); no extrapolation" % (
+                                       steps_run, args.n, ", ".join("%.1f" % v for v in secs))},
         "e2e": {"value": rate, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
+def check_parity(n, results_by_index):
+    """Compare engine results at the golden theta points with the committed oracle output (N=16384 only)."""
+    path = GOLDEN % n
+    if not os.path.exists(path):
+        return None
+    gold = json.load(open(path))
+    rel_nll, rel_grad, pts = 0.0, 0.0, []
+    for pt in gold["points"]:
+        out = results_by_index.get(pt["index"])
+        if out is None:
+            continue
+        g = np.concatenate([out["d_w"], [out["d_sigma_f2"]], out["d_noise"], out["d_beta"]])
+        gr = np.concatenate([np.asarray(pt["d_w"]), [pt["d_sigma_f2"]], np.asarray(pt["d_noise"]), np.asarray(pt["d_beta"])])
+        rel_nll = max(rel_nll, abs(out["nll"] - pt["nll"]) / abs(pt["nll"]))
+        rel_grad = max(rel_grad, float(np.max(np.abs(g - gr)) / np.max(np.abs(gr))))
+        pts.append(pt["index"])
+    par = {"rel_nll": rel_nll, "rel_grad": rel_grad, "points": pts, "tol_nll": 1e-9, "tol_grad": 1e-8,
+           "against": "tests/golden/c4_n%d_matern52.json (CPU oracle at the full size; point 1 is the first timed theta)" % n}
+    if not (rel_nll <= 1e-9 and rel_grad <= 1e-8):
+        raise SystemExit("bench.py: parity check FAILED against the committed oracle output: %s" % json.dumps(par))
+    return par
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from gpplus_b200 import _engine as E
-    from gpplus_b200.models import GP_Plus
     from gpplus_b200.models.gpregression import set_default_device
+    from gpplus_b200.optim.mll_scipy import MLLObjective
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -200,10 +220,9 @@ def run_ours(args):
     set_default_device(local)
 
     n = args.n
-    X, y = make_workload(n)
-    model = GP_Plus(torch.from_numpy(X), torch.from_numpy(y), dtype=torch.float64,
-                    quant_correlation_class="Matern52Kernel")
-    obj, thetas = theta_points(model, args.warmup + args.steps, seed=rank)
+    model = W.c4_model(n)
+    thetas = W.c4_theta_points(model)
+    obj = MLLObjective(model, True, [0, 0])
     eng = model._get_engine()
 
     def barrier():
@@ -213,25 +232,30 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident arm: X, y already in HBM, one gpp_mll_grad per step -------------------------------
-    hypers = [natural_from_theta(t) for t in thetas]
     for k in range(args.warmup):
-        eng.mll_grad(hypers[k], want_grad=True)
+        eng.mll_grad(W.c4_natural(step_theta(thetas, -1 - k, rank)), want_grad=True)
+    hypers = [W.c4_natural(step_theta(thetas, k, rank)) for k in range(args.steps)]
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
     barrier()
+    st0 = eng.stats()
     l0 = E.launch_count()
     t0 = time.time()
     stage = {k: 0.0 for k in ("covariance", "cholesky", "trtri", "solve", "lauum", "gradient", "total")}
-    for k in range(args.warmup, args.warmup + args.steps):
+    first_out = None
+    for k in range(args.steps):
         out = eng.mll_grad(hypers[k], want_grad=True)
+        if k == 0:
+            first_out = out
         tm = eng.timings()  # CUDA events recorded on the engine's own stream inside the call
         for s in stage:
             stage[s] += tm[s]
     barrier()
     t1 = time.time()
     launches = E.launch_count() - l0
+    st1 = eng.stats()
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     # two clocks, both max over ranks: wall time between the barriers (what `value` uses: it contains everything a
     # caller pays) and the device time of the K steps from CUDA events recorded on the engine's own stream
@@ -248,11 +272,11 @@ def run_ours(args):
     # that is the call timed here.  MLLObjective.fun (torch path, +1.4 ms of host work) returns the same values.
     objective = obj.fun_fast if obj.enable_fast_path() else obj.fun
     for k in range(min(2, args.warmup)):
-        objective(thetas[k])
+        objective(step_theta(thetas, -1 - k, rank))
     barrier()
     t0 = time.time()
-    for k in range(args.warmup, args.warmup + args.steps):
-        f, g = objective(thetas[k])
+    for k in range(args.steps):
+        f, g = objective(step_theta(thetas, k, rank))
     barrier()
     e2e_elapsed = torch.tensor([time.time() - t0], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -261,10 +285,58 @@ def run_ours(args):
     h2d = 8 * (eng.dq + eng.n_combo * eng.dz + eng.n_noise + eng.n_mean + 2)
     d2h = 8 * (4 + eng.dq + eng.n_noise + eng.n_mean) + 4
 
+    # ---- the sharded workloads of the metric's second half, in the same torchrun world (every rank takes part) ----
+    extra = {}
+    if not args.no_extras:
+        model.release_engine()
+        eng = None
+        barrier()
+        extra["fit_c2"] = fit_core(args, world, rank, local, "c2", 0)
+        barrier()
+        extra["acq_c5"] = acq_core(args, world, rank, local, steps=3)
+        barrier()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+
+    # ---- parity at the timed points + the SURVEY 8(d) protocol over all 65 prior draws (rank 0, untimed region) ----
+    if eng is None:
+        eng = model._get_engine()
+    results = {1: first_out, 0: eng.mll_grad(W.c4_natural(thetas[0]), want_grad=True),
+               2: eng.mll_grad(W.c4_natural(thetas[2]), want_grad=True)}
+    parity = check_parity(n, results)
+    t_init = []
+    for _ in range(3):
+        eng.mll_grad(W.c4_natural(thetas[0]), want_grad=True)
+        t_init.append(eng.timings()["total"])
+    per_draw, retried = [], []
+    sa = eng.stats()
+    for k in range(1, 1 + W.N_PRIOR_DRAWS):
+        s_before = eng.stats()["jitter_retries"]
+        tq = time.time()
+        try:
+            eng.mll_grad(W.c4_natural(thetas[k]), want_grad=True)
+            ok = True
+        except (E.NotPSDError, E.NanError):
+            ok = False
+        ms = 1e3 * (time.time() - tq)
+        r = eng.stats()["jitter_retries"] - s_before
+        (retried if (r > 0 or not ok) else per_draw).append((ms, r))
+    sb = eng.stats()
+    clean = [m for m, _ in per_draw]
+    n_retry = sum(r for _, r in retried)
+    prior_draws = {
+        "n": W.N_PRIOR_DRAWS, "median_ms": statistics.median(clean) if clean else None,
+        "mean_ms": sum(clean) / len(clean) if clean else None, "draws_needing_jitter": len(retried),
+        "retries": int(sb["jitter_retries"] - sa["jitter_retries"]), "early_outs": int(sb["early_outs"] - sa["early_outs"]),
+        "ms_per_retry": ((sum(m for m, _ in retried) - len(retried) * statistics.median(clean)) / n_retry)
+        if (n_retry > 0 and clean) else None,
+        "theta_init_ms": statistics.median(t_init),
+        "note": "wall ms per evaluation at every seeded prior draw; evaluations that needed the jitter ladder are "
+                "counted separately (a failed rung costs covariance + factorisation only: the status is read back "
+                "before the inverse / K^-1 / gradient are enqueued)"}
 
     # ---- roofline of the dominant kernel (dgemm_dmma_kernel: Cholesky trailing updates, L^-1, K^-1) --------
     peak = measure_fp64_peak(local)
@@ -296,30 +368,32 @@ def run_ours(args):
         "stages_ms": stage,
         # the leading part of L^-1 runs on a low-priority stream behind the factorisation (trtri_early), so the
         # event split between "cholesky" and "trtri" is not a split of work; their sum is (GPP_OVERLAP_INV=0
-        # separates them: 53.4 + 44.1 ms at N=16384)
+        # separates them)
         "stage_tflops": {"cholesky_plus_trtri": 2 * n3 / 3 / ((stage["cholesky"] + stage["trtri"]) * 1e-3) / 1e12,
                          "lauum": n3 / 3 / (stage["lauum"] * 1e-3) / 1e12},
         "hbm_stage_gbs": {"covariance": 4.0 * n * (n + 1) / (stage["covariance"] * 1e-3) / 1e9,
                           "gradient": 4.0 * n * (n + 1) / (stage["gradient"] * 1e-3) / 1e9},
     }
 
-    # ---- CPU baseline: the oracle on this box's host cores, bounded sample -------------------------------
-    cores = os.cpu_count() or 1
-    n_sample = min(n, 4096)
-    rate, t_step, threads = cpu_oracle_rate(n_sample, 2, 1, n, cores)
-    cpu = {"value": rate, "unit": "evals/s", "cores": threads, "kind": "port",
-           "sample": "2 oracle MLL+grad evals on the first %d points of the workload (%.2f s each), scaled by "
-                     "(N/%d)^3 to N=%d" % (n_sample, t_step, n_sample, n)}
+    # ---- CPU baseline: the oracle on this box's host cores, ONE real full-size evaluation (N=1 runs only) ----
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        secs, outs, threads = oracle_full_size(n, [thetas[1]], cores)
+        cpu = {"value": 1.0 / secs[0], "unit": "evals/s", "cores": threads, "kind": "port",
+               "sample": "1 real oracle MLL+grad evaluation at the full N=%d on the first timed theta (%.1f s); no "
+                         "extrapolation" % (n, secs[0]),
+               "oracle_vs_engine_rel_nll": abs(outs[0]["nll"] - first_out["nll"]) / abs(outs[0]["nll"])}
 
     line = {
-        "metric": "MLL+grad evals/sec (N=16k, fp64)", "value": value, "unit": "evals/s", "n_gpus": world,
+        "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps,
         "device_ms_per_step": 1e3 * device_elapsed / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "synthetic exact GP N=%d D=10 Matern-5/2 FP64 MLL+gradient" % n,
-                   "parallelism": "independent restarts, one per GPU (no data-path collective)",
-                   "l2": "inputs larger than L2: each step streams three %.1f GiB work matrices" % (8.0 * n * n / 2 ** 30),
-                   "nll_last": out["nll"]},
+        "config": bench_config(n),
+        "parallelism": "independent restarts, one per GPU (no data-path collective)",
+        "nll_first_step": first_out["nll"],
+        "jitter_retries_in_timed_region": int(st1["jitter_retries"] - st0["jitter_retries"]),
         "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "the objective fit_model_scipy hands to scipy: theta (host, float64) -> float32 cast, raw->natural "
                        "transforms, device evaluation, priors and chain rule (gpp_objective) -> (value, gradient) on "
@@ -328,11 +402,13 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "parity": parity,
+        "prior_draws": prior_draws,
+        "extra": extra,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
-
 
 
 # ------------------------------------------------------------------------------------------------
@@ -364,52 +440,71 @@ def _c2_problem():
     return Xtr, ytr, Xte, yte, qd
 
 
-def run_fit(args):
-    """64-restart multi-start MAP fit (fit_model_scipy, L-BFGS-B, reference defaults) of configs[1]."""
+def fit_core(args, world, rank, local, fit_config, maxiter):
+    """64-restart multi-start MAP fit (fit_model_scipy, L-BFGS-B, reference defaults) in the current process group:
+    restarts are claimed from the cross-rank work queue.  Returns the result dictionary on every rank."""
     import torch
     from gpplus_b200 import _engine as E
     from gpplus_b200.models import GP_Plus
-    from gpplus_b200.models.gpregression import set_default_device
     from gpplus_b200.optim import fit_model_scipy
-    from gpplus_b200.optim.mll_scipy import MLLObjective, _sample_from_prior
-    if args.impl == "reference":
-        return run_fit_reference(args)
-    world, rank, local = _dist_setup()
-    set_default_device(local)
-    options = {"maxiter": args.maxiter} if args.maxiter > 0 else {}
-    if args.fit_config == "c4":
-        X, y = make_workload(args.n)
+    from gpplus_b200.optim.mll_scipy import _sample_from_prior
+    options = {"maxiter": maxiter} if maxiter > 0 else {}
+    if fit_config == "c4":
+        X, y = W.c4_workload(args.n)
         Xtr, ytr = torch.from_numpy(X[: args.n - 256]), torch.from_numpy(y[: args.n - 256])
         Xte, yte = torch.from_numpy(X[args.n - 256:]), torch.from_numpy(y[args.n - 256:])
         model = GP_Plus(Xtr, ytr, dtype=torch.float64, quant_correlation_class="Matern52Kernel")
         what = "synthetic wing N=%d D=10 Matern-5/2, %d restarts (+1), L-BFGS-B%s" % (
-            Xtr.shape[0], args.restarts, " maxiter=%d" % args.maxiter if args.maxiter > 0 else " reference defaults")
+            Xtr.shape[0], args.restarts, " maxiter=%d" % maxiter if maxiter > 0 else " reference defaults")
     else:
         Xtr, ytr, Xte, yte, qd = _c2_problem()
         model = GP_Plus(Xtr, ytr, qual_dict=qd, dtype=torch.float64)
         what = "borehole mixed-variable, n=%d, 2 categorical x 5 levels, rough-RBF x latent map, %d restarts (+1), " \
                "L-BFGS-B reference defaults" % (Xtr.shape[0], args.restarts)
     torch.manual_seed(0)
-    obj = MLLObjective(model, True, [0, 0])
     theta0 = [_sample_from_prior(model) for _ in range(args.restarts + 1)]
     fit_model_scipy(model, num_restarts=0, theta0_list=theta0[:world], options={"maxiter": 1})  # warm-up
     torch.cuda.synchronize()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
     l0 = E.launch_count()
     t0 = time.time()
     res, best = fit_model_scipy(model, add_prior=True, num_restarts=args.restarts, theta0_list=theta0, options=options)
     torch.cuda.synchronize()
-    dt = time.time() - t0
+    dt = torch.tensor([time.time() - t0], dtype=torch.float64, device="cuda")
+    mine = torch.tensor([float(sum(1 for r in res if not isinstance(r, Exception) and
+                                   getattr(r, "message", "") != "gathered from another rank"))],
+                        dtype=torch.float64, device="cuda")
+    per_rank = [mine.clone() for _ in range(world)]
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dist.all_gather(per_rank, mine)
+    dt = float(dt)
+    nfev = sum(int(r.nfev) for r in res if not isinstance(r, Exception))
+    failed = sum(1 for r in res if isinstance(r, Exception))
+    mu = model.predict(Xte, return_std=False)
+    rrmse = float(torch.sqrt(torch.mean((mu - yte) ** 2)) / yte.std())
+    model.release_engine()
+    return {"metric": "64-restart fit time", "value": dt, "unit": "s", "n_gpus": world, "higher_is_better": False,
+            "scaling": "strong", "dtype": "f64", "data": "synthetic", "config": {"workload": what},
+            "objective_evals": nfev, "evals_per_s": nfev / dt, "failed_starts": failed,
+            "best_neg_log_posterior": float(best), "test_rrmse": rrmse,
+            "restarts_run_per_rank": [int(float(v)) for v in per_rank],
+            "gpu_launches_rank0": E.launch_count() - l0}
+
+
+def run_fit(args):
+    """``--workload fit``: the 64-restart fit alone (configs[1] by default, ``--fit-config c4`` for configs[3])."""
+    from gpplus_b200.models.gpregression import set_default_device
+    if args.impl == "reference":
+        return run_fit_reference(args)
+    world, rank, local = _dist_setup()
+    set_default_device(local)
+    out = fit_core(args, world, rank, local, args.fit_config, args.maxiter)
     if rank == 0:
-        nfev = sum(int(r.nfev) for r in res if not isinstance(r, Exception))
-        failed = sum(1 for r in res if isinstance(r, Exception))
-        mu = model.predict(Xte, return_std=False)
-        rrmse = float(torch.sqrt(torch.mean((mu - yte) ** 2)) / yte.std())
-        print(json.dumps({
-            "metric": "64-restart fit time", "value": dt, "unit": "s", "n_gpus": world, "higher_is_better": False,
-            "scaling": "strong", "dtype": "f64", "data": "synthetic",
-            "config": {"workload": what},
-            "objective_evals": nfev, "evals_per_s": nfev / dt, "failed_starts": failed, "best_neg_log_posterior": best,
-            "test_rrmse": rrmse, "gpu_launches": E.launch_count() - l0}), flush=True)
+        print(json.dumps(out), flush=True)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
@@ -455,21 +550,17 @@ def run_fit_reference(args):
     }), flush=True)
 
 
-def run_acq(args):
+def acq_core(args, world, rank, local, steps):
     """MFBO borehole (Example 04): predictive mean/variance + cost-aware acquisition + arg-max over M candidates,
-    candidates sharded over ranks."""
+    candidates sharded over the ranks of the current process group.  Returns the result dictionary on every rank."""
     import torch
-    from gpplus_b200 import _engine as E
     from gpplus_b200.bayesian_optimizations import (acquisition_table_argmax, prepare_candidate_table,
                                                     score_prepared, to_device)
     from gpplus_b200.models import GP_Plus
-    from gpplus_b200.models.gpregression import set_default_device
     from gpplus_b200.optim import fit_model_scipy
     from gpplus_b200.preprocessing.normalizeX import standard
     from gpplus_b200.test_functions.multi_fidelity import BH_MAX, BH_MIN, Borehole_MF_BO
     from scipy.stats.qmc import Sobol, scale
-    world, rank, local = _dist_setup()
-    set_default_device(local)
     np.random.seed(0)
     torch.manual_seed(0)
     qd = {8: 5}
@@ -496,7 +587,7 @@ def run_acq(args):
 
     # end-to-end arm: candidate table in HOST memory (ordering, level lookup, H2D, scoring, arg-max over ranks)
     e2e_times = []
-    for _ in range(max(1, args.steps)):
+    for _ in range(max(1, steps)):
         sync_all()
         t0 = time.time()
         score, idx, order = acquisition_table_argmax(model, table, best, costs, maximize=False)
@@ -506,7 +597,7 @@ def run_acq(args):
     prep = to_device(prepare_candidate_table(model, table, 5), local)
     score_prepared(model, prep, best, costs, maximize=False)
     dev_times = []
-    for _ in range(max(3, args.steps)):
+    for _ in range(max(3, steps)):
         sync_all()
         t0 = time.time()
         score_d, idx_d = score_prepared(model, prep, best, costs, maximize=False)
@@ -518,23 +609,29 @@ def run_acq(args):
         import torch.distributed as dist
         dist.all_reduce(both, op=dist.ReduceOp.MAX)
     dt_e2e, dt_dev = float(both[0]), float(both[1])
+    n_tr = int(U.shape[0])
+    model.release_engine()
+    return {
+        "metric": "acquisition candidates/sec (predict mean/var + AF + arg-max)", "value": M / dt_dev,
+        "unit": "candidates/s", "n_gpus": world, "higher_is_better": True, "scaling": "strong", "dtype": "f64",
+        "data": "synthetic", "ms_per_step": 1e3 * dt_dev,
+        "config": {"workload": "MFBO borehole, n_train=%d, 5 sources, %d Sobol candidates split in contiguous "
+                               "chunks over the ranks; value: chunks resident in HBM" % (n_tr, M)},
+        "e2e": {"value": M / dt_e2e, "unit": "candidates/s", "ms_per_step": 1e3 * dt_e2e,
+                "h2d_bytes_per_step": int(M * (8 * 8 + 4 + 4)), "d2h_bytes_per_step": 16,
+                "api": "bayesian_optimizations.acquisition_table_argmax(model, table) from HOST memory: "
+                       "source-major ordering, level lookup, H2D, fused predict+AF+arg-max, arg-max over ranks"},
+        "best": {"score": score, "index": int(idx), "table_row": int(order[int(idx)])}}
+
+
+def run_acq(args):
+    """``--workload acq``: BASELINE configs[4] alone."""
+    from gpplus_b200.models.gpregression import set_default_device
+    world, rank, local = _dist_setup()
+    set_default_device(local)
+    out = acq_core(args, world, rank, local, args.steps)
     if rank == 0:
-        n_tr = int(U.shape[0])
-        print(json.dumps({
-            "metric": "acquisition candidates/sec (predict mean/var + AF + arg-max)", "value": M / dt_dev,
-            "unit": "candidates/s", "n_gpus": world, "higher_is_better": True, "scaling": "strong", "dtype": "f64",
-            "data": "synthetic", "ms_per_step": 1e3 * dt_dev,
-            "config": {"workload": "MFBO borehole, n_train=%d, 5 sources, %d Sobol candidates split in contiguous "
-                                   "chunks over the ranks; value: chunks resident in HBM" % (n_tr, M)},
-            "e2e": {"value": M / dt_e2e, "unit": "candidates/s", "ms_per_step": 1e3 * dt_e2e,
-                    "h2d_bytes_per_step": int(M * (8 * 8 + 4 + 4)), "d2h_bytes_per_step": 16,
-                    "api": "bayesian_optimizations.acquisition_table_argmax(model, table) from HOST memory: "
-                           "source-major ordering, level lookup, H2D, fused predict+AF+arg-max, arg-max over ranks"},
-            "roofline": {"bound": "hbm", "unit": "GB/s", "peak": 6463.3,
-                         "achieved": M / world * (8.0 * 128 * 2 + 8 * 8 + 24) / dt_dev / 1e9,
-                         "note": "per GPU: K* chunk written then read once (2 x 8 x Np bytes per candidate, Np=128) "
-                                 "+ inputs and results"},
-            "best": {"score": score, "index": int(idx)}}), flush=True)
+        print(json.dumps(out), flush=True)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
@@ -556,6 +653,9 @@ def main():
     ap.add_argument("--fit-config", default="c2", choices=["c2", "c4"],
                     help="fit workload: c2 = borehole mixed n=500 (configs[1]); c4 = synthetic N=--n D=10 Matern-5/2 (configs[3])")
     ap.add_argument("--candidates", type=int, default=1000000)
+    ap.add_argument("--no-extras", action="store_true",
+                    help="mll workload: skip extra.fit_c2 / extra.acq_c5 (the sharded workloads of the metric's second half)")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="mll workload: skip the full-size CPU oracle evaluation")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours" and args.workload == "mll":
         args.warmup = 3

@@ -21,7 +21,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libg
 
 EXPORTS = (
     "gpp_version", "gpp_device_count", "gpp_last_error", "gpp_launch_count", "gpp_create", "gpp_destroy", "gpp_mll_grad",
-    "gpp_get_timings", "gpp_covariance", "gpp_fetch", "gpp_factorize", "gpp_predict", "gpp_acq_argmax",
+    "gpp_get_timings", "gpp_get_stats", "gpp_covariance", "gpp_fetch", "gpp_factorize", "gpp_predict", "gpp_acq_argmax",
     "gpp_probe_dgemm", "gpp_set_theta_layout", "gpp_objective",
 )
 
@@ -76,6 +76,11 @@ class _Timings(C.Structure):
                 ("lauum", C.c_float), ("gradient", C.c_float), ("total", C.c_float)]
 
 
+class _Stats(C.Structure):
+    _fields_ = [("evaluations", C.c_int64), ("factorizations", C.c_int64), ("jitter_retries", C.c_int64),
+                ("early_outs", C.c_int64)]
+
+
 _lib = None
 _lib_lock = threading.Lock()
 
@@ -103,6 +108,8 @@ def load_library():
         lib.gpp_mll_grad.restype = C.c_int
         lib.gpp_get_timings.argtypes = [C.c_void_p, C.POINTER(_Timings)]
         lib.gpp_get_timings.restype = C.c_int
+        lib.gpp_get_stats.argtypes = [C.c_void_p, C.POINTER(_Stats)]
+        lib.gpp_get_stats.restype = C.c_int
         lib.gpp_covariance.argtypes = [C.c_void_p, C.POINTER(_Hyper), C.c_void_p]
         lib.gpp_covariance.restype = C.c_int
         lib.gpp_fetch.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
@@ -326,6 +333,13 @@ class Engine:
             _raise(rc, "gpp_get_timings")
         return {k: float(getattr(t, k)) for k, _ in _Timings._fields_}
 
+    def stats(self) -> Dict[str, int]:
+        st = _Stats()
+        rc = self._lib.gpp_get_stats(self._h, C.byref(st))
+        if rc != GPP_OK:
+            _raise(rc, "gpp_get_stats")
+        return {k: int(getattr(st, k)) for k, _ in _Stats._fields_}
+
     def covariance(self, hyper: Dict) -> np.ndarray:
         hy, keep = self._hyper(hyper)
         out = np.empty((self.n, self.n))
@@ -336,8 +350,8 @@ class Engine:
         return out
 
     def fetch(self, which: str) -> np.ndarray:
-        code = {"L": 0, "Linv": 1, "Kinv": 2, "alpha": 3}[which]
-        out = np.empty(self.n if code == 3 else (self.n, self.n))
+        code = {"L": 0, "Linv": 1, "Kinv": 2, "alpha": 3, "Kinv_diag": 4}[which]
+        out = np.empty(self.n if code >= 3 else (self.n, self.n))
         rc = self._lib.gpp_fetch(self._h, code, _ptr(out))
         if rc != GPP_OK:
             _raise(rc, "gpp_fetch")

@@ -15,7 +15,8 @@ inner steps are re-pointed at the B200 engine:
 Deviations from the reference source, which cannot run as published: it constructs the model with
 ``GP_Plus(Xtrain, ytrain, qual_index, IS=IS)`` although ``GP_Plus`` has neither a third positional
 ``qual_index`` nor an ``IS`` argument (models/gp_plus.py:79-108); here the model is built with
-``qual_dict=qual_index, interval_score=IS``.  Quirks that change results are kept and marked QUIRK.
+``qual_dict=qual_index, interval_score=IS``.  Quirks that change results are kept and marked QUIRK; the one
+deliberate deviation (arg-max over every source) is documented on ``acquisition_table_argmax``.
 """
 from __future__ import annotations
 
@@ -66,8 +67,9 @@ def prepare_candidate_table(model, table_x, n_src: int) -> Dict:
         if len(cols) > 0:
             torch.index_select(part, 1, cols_t, out=xq_t[a - lo:b - lo])
         if has_lvl:
-            # QUIRK: eval-mode setlevels ranks the categorical columns of each per-source slice (gp_plus.py:1081);
-            # the labels come from the WHOLE slice so that a chunk of it is ranked identically
+            # eval-mode setlevels ranks the categorical columns of [train_inputs, per-source slice]
+            # (gp_plus.py:1081 under ExactGP.__call__); the slice's labels come from the WHOLE slice so that a
+            # chunk of it is ranked identically
             labels = _slice_labels(model, x, per_src[s])
             lvl[a - lo:b - lo] = model._level_index(part, False, relevel_labels=labels)
         mi = model._mean_index(part)
@@ -116,11 +118,15 @@ def prepare_candidate_table_on_device(model, table_x, n_src: int, device: int) -
             sl = slice(a - lo, b - lo)
             ranked = cat[sl]
             if model.relevel_on_predict:
-                # QUIRK: eval-mode setlevels ranks every categorical column inside each per-source slice
-                # (gp_plus.py:1081); the labels are those of the WHOLE slice, not of this rank's chunk
+                # eval-mode setlevels ranks every categorical column of [train_inputs, per-source slice]
+                # (gp_plus.py:1081 under ExactGP.__call__); the labels are those of the WHOLE slice, not of this
+                # rank's chunk
                 whole = x.index_select(0, order[int(bounds[s]):int(bounds[s + 1])])[:, cat_cols].to(torch.int64)
-                ranked = torch.stack([torch.searchsorted(torch.unique(whole[:, k]), cat[sl][:, k].contiguous())
-                                      for k in range(len(cat_cols))], dim=1)
+                train_labels = model._train_labels()
+                ranked = torch.stack([
+                    torch.searchsorted(torch.unique(torch.cat([torch.as_tensor(train_labels[k], device=dev),
+                                                               whole[:, k]])), cat[sl][:, k].contiguous())
+                    for k in range(len(cat_cols))], dim=1)
             lev_t = torch.as_tensor(levels, device=dev)
             if bool(((ranked < 0) | (ranked >= lev_t[None, :])).any()):
                 raise ValueError("The categorical input (or source indices) are not defined properly. They should be "
@@ -179,9 +185,14 @@ def acquisition_table_argmax(model, table_x, best_values: Sequence[float], cost_
 
     ``table_x`` [M, d] holds model inputs whose LAST column is the source index.  Candidates are scored in
     source-major order -- all rows of source 0 (AF_HF_Engineering), then source 1, ... (AF_LF_Engineering) --
-    exactly the order of ``torch.cat(scores)`` in the reference, with ``include_noise=False``.  Returns
+    with ``include_noise=False``, each slice scored exactly as the reference scores it.  Returns
     ``(best_score, index_in_source_major_order, order)`` where ``order`` maps that position back to a row of
     ``table_x``; with ``return_scores`` the source-major score vector of THIS rank's chunk is appended.
+
+    DELIBERATE DEVIATION: the reference resets ``scores = []`` inside its per-source loop (BO_GP_plus.py:183), so
+    its ``torch.argmax(torch.cat(scores))`` only ever sees the LAST source's slice and then indexes the original
+    table with that slice-local position.  Here the arg-max covers every source (what the loop evidently intends)
+    and callers map the winning position back to its table row through ``order``.
     """
     eng = model._ensure_factor()
     if torch.cuda.is_available() and os.environ.get("GPPLUS_TABLE_PREP", "device") == "device":
@@ -304,12 +315,14 @@ def BO(Xtrain=None, ytrain=None, costs=None, l_bound=None, u_bound=None, xmean=N
             if converged():
                 break
             model = fit_new_model(Xtrain, ytrain)
-            _, index, _ = acquisition_table_argmax(model, table[:, 0:-1], best_values, cost_by_source,
-                                                   maximize=maximize_flag)
+            _, index, order = acquisition_table_argmax(model, table[:, 0:-1], best_values, cost_by_source,
+                                                       maximize=maximize_flag)
             model.release_engine()
-            # QUIRK: the arg-max position in source-major order indexes the ORIGINAL table (:194-196)
-            Xnew = torch.tensor(table[index][0:-1])
-            ynew = table[index][-1]
+            # the winning source-major position is mapped back to the row of the table that was scored (the
+            # reference indexes the original table with a slice-local position, see acquisition_table_argmax)
+            row = int(order[index])
+            Xnew = torch.tensor(table[row][0:-1])
+            ynew = table[row][-1]
             Xtrain = torch.cat([Xtrain, Xnew.reshape(1, -1)])
             ytrain = torch.cat([ytrain, torch.tensor(ynew).reshape(-1)], dim=0)
             ymin_list.append(np.asarray(ynew).reshape(-1))

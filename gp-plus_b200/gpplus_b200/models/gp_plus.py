@@ -46,8 +46,10 @@ def _rough_ls_inv(x):
 class GP_Plus(GPR):
     """See the reference docstring (models/gp_plus.py:45-78) for the meaning of every argument."""
 
-    # eval-mode quirk of the reference kept by default: categorical columns of prediction inputs are
-    # re-ranked with ``setlevels`` before the level lookup (models/gp_plus.py:1081-1082)
+    # eval-mode behaviour of the reference kept by default: gpytorch's ExactGP.__call__ hands forward() the
+    # concatenation [train_inputs, Xtest], and transform_categorical re-ranks its categorical columns with
+    # ``setlevels`` (models/gp_plus.py:1081-1082).  Prediction categories are therefore ranked against the sorted
+    # unique values of train U test per column -- the identity whenever training holds every level 0..L-1.
     relevel_on_predict = True
 
     def __init__(
@@ -254,21 +256,23 @@ class GP_Plus(GPR):
         """Row of the level-combination table per point (perm_dict lookup, gp_plus.py:1085) -- vectorised
         mixed-radix index, identical to the itertools.product order of ``zeta_matrix``.
 
-        ``relevel_labels`` (one sorted array of unique values per categorical column) replaces the eval-mode
-        ``setlevels`` ranking computed from ``x`` itself: callers that score a slice of a larger batch pass the
-        labels of the whole batch so that the slice is ranked exactly as the reference would rank the batch."""
+        In eval mode the reference ranks the categorical columns of ``[train_inputs, x]`` (see
+        ``relevel_on_predict``); ``relevel_labels`` (one array of values per categorical column) replaces the
+        values of ``x`` in that union: callers that score a chunk of a larger batch pass the labels of the whole
+        batch so that the chunk is ranked exactly as the reference would rank the batch."""
         if self._level_strides is None:
             return None
         cols = self.qual_kernel_columns[-1]
-        if not training and self.relevel_on_predict and relevel_labels is not None:
-            raw = x[:, cols].detach().cpu().numpy()
-            c = np.stack([np.searchsorted(np.asarray(relevel_labels[k]), raw[:, k]) for k in range(len(cols))],
-                         axis=1).astype(np.int64)
+        cat = x[:, cols].detach().cpu().type(torch.int64).numpy()
+        if not training and self.relevel_on_predict:
+            train_labels = self._train_labels()
+            c = np.empty_like(cat)
+            for k in range(len(cols)):
+                seen = cat[:, k] if relevel_labels is None else np.asarray(relevel_labels[k], dtype=np.int64)
+                union = np.union1d(train_labels[k], seen)
+                c[:, k] = np.searchsorted(union, cat[:, k])
         else:
-            cat = x[:, cols].clone().type(torch.int64)
-            if not training and self.relevel_on_predict:
-                cat = torch.as_tensor(setlevels(cat)).type(torch.int64)
-            c = cat.cpu().numpy()
+            c = cat
         levels, strides = self._level_strides
         if (c < 0).any() or (c >= levels[None, :]).any():
             raise ValueError("The categorical input (or source indices) are not defined properly. They should be "
@@ -276,9 +280,19 @@ class GP_Plus(GPR):
                              "function, which is a preprocessing function.")
         return (c * strides[None, :]).sum(1).astype(np.int32)
 
+    def _train_labels(self):
+        """Sorted unique values (int64) of every categorical column of the training inputs."""
+        cached = self.__dict__.get("_train_labels_cache")
+        if cached is None:
+            cols = self.qual_kernel_columns[-1]
+            cat = self.train_inputs[0][:, cols].detach().cpu().type(torch.int64).numpy()
+            cached = [np.unique(cat[:, k]) for k in range(len(cols))]
+            self.__dict__["_train_labels_cache"] = cached
+        return cached
+
     def _relevel_labels(self, x: torch.Tensor):
-        """Sorted unique values of every categorical column of ``x`` truncated to int64 (what eval-mode
-        ``setlevels`` would rank by), or None when the model has no categorical input."""
+        """Unique values of every categorical column of ``x`` truncated to int64 (the part of the eval-mode
+        ``setlevels`` ranking contributed by ``x``), or None when the model has no categorical input."""
         if self._level_strides is None:
             return None
         cols = self.qual_kernel_columns[-1]
@@ -478,16 +492,9 @@ class GP_Plus(GPR):
         mu = (mean - self.y_min) / self.y_std
         sd = std / self.y_std
         xtr = self.train_inputs[0].detach().double().cpu()
-        if self._level_strides is not None and self.relevel_on_predict:
-            # the joint evaluation must see the test categories exactly as predict() does (eval-mode re-ranking)
-            saved = self.relevel_on_predict
-            lv_te = self._level_index(Xtest, False)
-            self.relevel_on_predict = False
-            try:
-                lv_tr = self._level_index(xtr, True)
-            finally:
-                self.relevel_on_predict = saved
-            joint_levels = np.concatenate([lv_tr, lv_te])
+        if self._level_strides is not None:
+            # the joint evaluation must see the test categories exactly as predict() does (eval-mode ranking)
+            joint_levels = np.concatenate([self._level_index(xtr, True), self._level_index(Xtest, False)])
         else:
             joint_levels = None
         nll_train = self._joint_nll_with_levels(xtr, self.train_targets, None, True)

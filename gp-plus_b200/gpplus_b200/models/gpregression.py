@@ -242,6 +242,26 @@ class GPR(Module):
         w, z, sf2, noise, beta = self._natural()
         return _EngineLogProb.apply(self, w, z, sf2, noise, beta)
 
+    def prior_mean_and_variance(self):
+        """Prior mean vector and prior variance (diag of sigma_f^2 * correlation = sigma_f^2) at the training inputs
+        as differentiable float64 tensors -- what ``model(*model.train_inputs)`` returns in training mode
+        (gp_plus.py:386-484); used by the interval-score penalty (mll_scipy.py:57-59)."""
+        x = self.train_inputs[0]
+        n = x.shape[0]
+        n_mean, consts = self._mean_layout()
+        if n_mean == 0:
+            mean = torch.zeros(n, dtype=torch.float64)
+        else:
+            beta = torch.cat([c.reshape(-1) for c in consts]).to(torch.float64)
+            idx = self._mean_index(x)
+            if idx is None:
+                mean = beta[0].expand(n)
+            else:
+                idx = torch.as_tensor(idx, dtype=torch.long)
+                mean = torch.where(idx >= 0, beta[idx.clamp_min(0)], torch.zeros(n, dtype=torch.float64))
+        var = self.covar_module.outputscale.to(torch.float64).reshape(()).expand(n)
+        return mean, var
+
     def _hyper_numpy(self):
         with torch.no_grad():
             w, z, sf2, noise, beta = self._natural()

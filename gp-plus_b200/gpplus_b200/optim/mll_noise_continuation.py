@@ -22,7 +22,7 @@ def loocv_rrmse(model) -> float:
         eng = model._get_engine()
         eng.mll_grad(model._hyper_numpy(), want_grad=True)  # leaves alpha and K_y^-1 on the device
         alpha = eng.fetch("alpha")
-        kinv_diag = np.diag(eng.fetch("Kinv"))
+        kinv_diag = eng.fetch("Kinv_diag")  # n doubles (a strided device copy), not the N x N matrix
     return float(np.sqrt(np.mean((alpha / kinv_diag) ** 2)))
 
 

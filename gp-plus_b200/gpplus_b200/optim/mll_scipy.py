@@ -11,8 +11,8 @@ What changed underneath: the objective is one ``gpp_mll_grad`` call (fused covar
 DMMA Cholesky, triangular inverse, fused gradient reduction) instead of a dense torch forward +
 autograd backward, and the joblib/loky process fan-out (:287-293) becomes a restart scheduler: host
 threads that each own a model copy and an engine handle, spread over the visible GPUs; under
-``torchrun`` the restart list is sharded across ranks (one GPU each) and only ``(nll, theta)`` of
-every restart is gathered (``parallel.gather_restarts``).
+``torchrun`` the restarts are claimed from a cross-rank work queue (``parallel.RestartQueue``; one GPU per
+rank) and only ``(nll, theta)`` of every restart is gathered (``parallel.gather_restarts``).
 """
 from __future__ import annotations
 
@@ -57,14 +57,13 @@ def marginal_log_likelihood(model, add_prior: bool, regularization_parameter=[0,
             l1 = l1 + torch.sum(torch.abs(param))
     out = out - (regularization_parameter[0] * l1 + regularization_parameter[1] * l2)
     if getattr(model, "interval_score", False) is True:
-        # leave-in predictive intervals at the training inputs (mll_scipy.py:57-59)
-        x = model.train_inputs[0]
-        was_training = model.training
-        mean, std = model.predict(x, return_std=True, include_noise=False)
-        model.train(was_training)
-        mu = (mean - model.y_min) / model.y_std
-        sd = std / model.y_std
-        score, _ = interval_score_function(mu + 1.96 * sd, mu - 1.96 * sd, model.y_scaled)
+        # mll_scipy.py:57-59: ``output = model(*model.train_inputs)`` is evaluated in TRAINING mode, i.e. it is the
+        # PRIOR at the training inputs: mean m(x_i) (the constant of the point's mean group) and variance
+        # diag(Sigma) = sigma_f^2 (clamped at settings.min_variance).  Both are differentiable functions of the raw
+        # parameters, so the penalty contributes to the gradient through the output scale and the mean constants.
+        mean, var = model.prior_mean_and_variance()
+        sd = var.clamp_min(gptsettings.min_variance).sqrt()
+        score, _ = interval_score_function(mean + 1.96 * sd, mean - 1.96 * sd, model.y_scaled)
         return out - 0.08 * torch.abs(out) * score
     return out
 
@@ -233,33 +232,32 @@ def _workers_per_gpu(n_train: int) -> int:
     return 1
 
 
-def _run_restarts(likobj, theta0_list, indices, jac, options, method, constraint, bounds, n_jobs) -> Dict[int, object]:
-    """Run the restarts ``indices`` of ``theta0_list`` on this process's GPUs; returns {index: result}."""
+def _run_restarts(likobj, theta0_list, work, jac, options, method, constraint, bounds, n_jobs) -> Dict[int, object]:
+    """Run restarts claimed from ``work`` (a ``parallel.RestartQueue`` shared by every rank) on this process's
+    GPUs; returns {index: result} of the restarts this process ran."""
     devices = parallel.local_devices()
     n_train = int(likobj.model.train_targets.shape[0])
     n_workers = len(devices) * _workers_per_gpu(n_train)
     if n_jobs is not None and n_jobs > 0:
         n_workers = min(n_workers, n_jobs)
-    n_workers = max(1, min(n_workers, len(indices)))
+    n_workers = max(1, min(n_workers, work.count))
     results: Dict[int, object] = {}
-    if len(indices) == 0:
+    if work.count == 0:
         return results
-    work: "queue.Queue[int]" = queue.Queue()
-    for i in indices:
-        work.put(i)
     errors: List[BaseException] = []
     lock = threading.Lock()
 
     def worker(slot: int):
         from ..models.gpregression import set_default_device
         set_default_device(devices[slot % len(devices)])
-        local = copy.deepcopy(likobj) if n_workers > 1 else likobj
+        local = None
         try:
             while True:
-                try:
-                    i = work.get_nowait()
-                except queue.Empty:
+                i = work.claim()
+                if i is None:
                     break
+                if local is None:
+                    local = copy.deepcopy(likobj) if n_workers > 1 else likobj
                 res = _fit_model_from_state(local, theta0_list[i], jac, options, method, constraint, bounds)
                 with lock:
                     results[i] = res
@@ -267,7 +265,7 @@ def _run_restarts(likobj, theta0_list, indices, jac, options, method, constraint
             with lock:
                 errors.append(e)
         finally:
-            if local is not likobj:
+            if local is not None and local is not likobj:
                 local.model.release_engine()
 
     if n_workers == 1:
@@ -316,8 +314,9 @@ def fit_model_scipy(
     # every rank must optimise from the same list: rank 0's draws win
     theta0_list = parallel.broadcast_theta_list(theta0_list)
 
-    mine = parallel.shard_indices(len(theta0_list))
-    local = _run_restarts(likobj, theta0_list, mine, jac, defaults, method, constraint, bounds, n_jobs)
+    # restarts are claimed from a cross-rank work queue (the reference: joblib's dynamic dispatch, :287-293)
+    work = parallel.RestartQueue(len(theta0_list))
+    local = _run_restarts(likobj, theta0_list, work, jac, defaults, method, constraint, bounds, n_jobs)
     out = parallel.gather_restarts(local, len(theta0_list), len(theta0_list[0]) if theta0_list else 0)
 
     nlls_opt = [np.inf if isinstance(res, Exception) else res.fun for res in out]

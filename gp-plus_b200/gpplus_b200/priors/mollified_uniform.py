@@ -42,7 +42,9 @@ class MollifiedUniformPrior(Prior, torch.distributions.Distribution):
         return tails.log_prob(outside) + self._log_normalization_constant
 
     def rsample(self, sample_shape=torch.Size([])):
-        return Uniform(self.a, self.b).rsample(sample_shape).to(self.a)
+        # drawn in float32 like the reference (its a / b are float32 tensors, priors/mollified_uniform.py:59,88):
+        # torch.rand consumes the generator differently per dtype, and restart points must be reproducible
+        return Uniform(self.a.float(), self.b.float()).rsample(sample_shape).to(self.a)
 
     def expand(self, expand_shape, _instance=None):
         shape = torch.Size(expand_shape)

@@ -114,6 +114,14 @@ typedef struct gpp_timings {
     float total;
 } gpp_timings;
 
+/* per-handle counters since gpp_create (bench.py reports jitter-ladder retries separately) */
+typedef struct gpp_stats {
+    int64_t evaluations;     /* gpp_mll_grad / gpp_objective / gpp_factorize calls */
+    int64_t factorizations;  /* Cholesky attempts (evaluations + jitter retries) */
+    int64_t jitter_retries;  /* attempts with jitter 1e-8 / 1e-7 / 1e-6 (psd_safe_cholesky ladder) */
+    int64_t early_outs;      /* failed attempts abandoned right after the factorisation */
+} gpp_stats;
+
 int gpp_version(void);
 int gpp_device_count(void);
 const char* gpp_last_error(void);
@@ -126,13 +134,15 @@ void gpp_destroy(gpp_handle* h);
 /* replaces MLLObjective.fun (optim/mll_scipy.py:112-127) */
 int gpp_mll_grad(gpp_handle* h, const gpp_hyper* hyper, int want_grad, gpp_mll_result* out);
 int gpp_get_timings(gpp_handle* h, gpp_timings* out);
+int gpp_get_stats(gpp_handle* h, gpp_stats* out);
 
 /* dense K (without noise) of the training inputs, k_out is [n*n] row-major
  * (covar_module(x).evaluate(), models/gp_plus.py:472-474) */
 int gpp_covariance(gpp_handle* h, const gpp_hyper* hyper, double* k_out);
 
 /* debugging / parity probes: copy the factor L (lower, [n*n]), its inverse, or K_y^{-1} of the
- * last evaluation back to the host.  which: 0 = L, 1 = L^{-1}, 2 = K_y^{-1}, 3 = alpha ([n]) */
+ * last evaluation back to the host.  which: 0 = L, 1 = L^{-1}, 2 = K_y^{-1}, 3 = alpha ([n]),
+ * 4 = diag(K_y^{-1}) ([n]; needs an evaluation with gradient; loocv_rrmse, optim/mll_noise_continuation.py:28-42) */
 int gpp_fetch(gpp_handle* h, int which, double* out);
 
 /* prediction: factorize once for fixed hyper-parameters (DefaultPredictionStrategy cache,

@@ -170,9 +170,11 @@ def neg_log_posterior(spec: Dict, theta: np.ndarray, add_prior: bool = True, the
 
         if len(qual) > 0:
             logp = logp + normal(0.0, 1.0).log_prob(params["latent" + str(qcols)]).sum()
-        if raw_noise is not None:
-            scale = 0.01
-            logp = logp + (torch.log(torch.log(1 + 3 * (scale / (lb + torch.exp(raw_noise))) ** 2)) + raw_noise).sum()
+        # marginal_log_likelihood adds EVERY registered prior (mll_scipy.py:40-43 has no requires_grad test): with
+        # fix_noise the horseshoe term of the frozen raw noise is a constant offset of the objective
+        scale = 0.01
+        rn = raw_noise if raw_noise is not None else torch.log(noise - lb)
+        logp = logp + (torch.log(torch.log(1 + 3 * (scale / (lb + torch.exp(rn))) ** 2)) + rn).sum()
         logp = logp + torch.distributions.LogNormal(torch.tensor(1e-6, dtype=torch.float64), torch.tensor(1.0, dtype=torch.float64)).log_prob(sf2).sum()
         if len(quant_cols) > 0:
             if kname == "RBFKernel":
@@ -184,6 +186,15 @@ def neg_log_posterior(spec: Dict, theta: np.ndarray, add_prior: bool = True, the
         for name, p in params.items():
             if name.startswith("mean_module"):
                 logp = logp + normal(0.0, 1.0).log_prob(p).sum()
+    if spec.get("interval_score", False):
+        # mll_scipy.py:57-59: interval score of the PRIOR at the training inputs (training-mode forward): mean and
+        # variance diag(Sigma), clamped at gpytorch's min_variance, against the scaled targets
+        var = torch.diagonal(Sigma).clamp_min(1e-10)
+        up, lo_ = mean + 1.96 * var.sqrt(), mean - 1.96 * var.sqrt()
+        sc = up - lo_
+        sc = sc + (y > up).to(torch.int64) * 2 / 0.05 * (y - up)
+        sc = sc + (y < lo_).to(torch.int64) * 2 / 0.05 * (lo_ - y)
+        logp = logp - 0.08 * torch.abs(logp) * sc.mean()
     obj = -logp
     if not want_grad:
         return float(obj)

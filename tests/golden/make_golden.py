@@ -1,6 +1,8 @@
 """Generate the golden fixtures in this directory from the CPU oracle (seeded, float64).
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py            # the small natural-parameter cases
+    python tests/golden/make_golden.py --c4 16384  # headline workload (bench.py asserts on it): ~3 min and ~25 GB
+                                                   # of host memory per evaluation point on 8 cores
 
 The reference itself cannot be imported in this image (gpytorch / botorch are not installed), so these
 vectors pin the ORACLE (regression) and give the GPU tests fixed targets; they are not outputs of the
@@ -55,5 +57,33 @@ def main():
         print(name, "nll", res["nll"])
 
 
+def main_c4(n, points=(0, 1, 2)):
+    """NLL + 13 gradient entries of the CPU oracle on the C4 workload of bench.py (bench_workloads.py) at
+    theta_init (point 0) and the first prior draws: the numbers bench.py and the -m gpu tests assert against."""
+    import json
+    import time
+    import bench_workloads as W
+    model = W.c4_model(256)  # the theta points depend on the priors only
+    thetas = W.c4_theta_points(model)
+    prob = W.c4_oracle_problem(n)
+    out = {"n": n, "workload": "bench_workloads.c4_workload", "oracle": "oracle.gp_oracle.mll(mode='expansion')",
+           "points": []}
+    for k in points:
+        t0 = time.time()
+        r = O.mll(prob, W.c4_natural(thetas[k]), want_grad=True)
+        out["points"].append({"index": int(k), "theta": [float(v) for v in thetas[k]], "nll": r["nll"],
+                              "quad": r["quad"], "logdet": r["logdet"], "jitter": r["jitter"],
+                              "d_w": [float(v) for v in r["d_w"]], "d_sigma_f2": r["d_sigma_f2"],
+                              "d_noise": [float(v) for v in r["d_noise"]], "d_beta": [float(v) for v in r["d_beta"]],
+                              "oracle_seconds": time.time() - t0})
+        print("c4 n=%d point %d nll %.9f (%.1f s)" % (n, k, r["nll"], time.time() - t0), flush=True)
+        with open(os.path.join(HERE, "c4_n%d_matern52.json" % n), "w") as f:
+            json.dump(out, f, indent=1)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 2 and sys.argv[1] == "--c4":
+        sys.path.insert(0, os.path.join(ROOT, "gp-plus_b200"))
+        main_c4(int(sys.argv[2]))
+    else:
+        main()

@@ -19,6 +19,13 @@ def test_reference_arm_prints_one_contract_line():
     assert d["value"] > 0 and d["config"]["workload"].startswith("synthetic exact GP N=256")
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # the steps reported are the evaluations really run at the FULL size (no extrapolation), and they fit the run
+    assert d["steps"] == 1 and d["steps_requested"] == 1 and d["warmup"] == 0
+    assert abs(d["ms_per_step"] * d["steps"] * 1e-3 - d["steps"] / d["value"]) < 1e-6
+    # both arms print the same config object
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.bench_config(256)
 
 
 def test_reference_arm_is_silent_on_other_ranks():

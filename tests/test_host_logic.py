@@ -187,6 +187,32 @@ thetas = parallel.broadcast_theta_list(thetas)
 assert all(np.all(t == i) for i, t in enumerate(thetas))
 mine = parallel.shard_indices(5)
 assert mine == list(range(rank, 5, 2))
+# cross-rank work queue: every index is claimed exactly once, whatever the interleaving
+import threading, time
+q = parallel.RestartQueue(23)
+claimed = []
+def _drain():
+    while True:
+        i = q.claim()
+        if i is None:
+            break
+        claimed.append(i)
+        time.sleep(0.001 * (1 + rank))
+ts = [threading.Thread(target=_drain) for _ in range(3)]
+[t.start() for t in ts]
+[t.join() for t in ts]
+flags = torch.zeros(23)
+flags[claimed] = 1.0
+assert len(claimed) == len(set(claimed))
+dist.all_reduce(flags)
+assert bool((flags == 1.0).all()), flags
+q2 = parallel.RestartQueue(1)   # a second queue uses a fresh counter
+got = q2.claim()
+total = torch.tensor([0.0 if got is None else 1.0])
+dist.all_reduce(total)
+assert float(total) == 1.0
+# ownership by claim order instead of i %% world: rank 0 owns {0, 1, 4}, rank 1 owns {2, 3}
+mine = [0, 1, 4] if rank == 0 else [2, 3]
 local = {}
 for i in mine:
     local[i] = NotPSDError("x") if i == 3 else OptimizeResult(x=thetas[i] + 0.5, fun=10.0 - i, nit=i, nfev=2 * i,

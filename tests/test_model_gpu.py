@@ -351,3 +351,77 @@ def test_constructor_variants_fit_through_the_native_objective(kwargs):
     mu, sd = m.predict(torch.tensor(X), return_std=True)
     assert bool(torch.all(torch.isfinite(mu))) and bool(torch.all(sd > 0))
     assert float(torch.sqrt(torch.mean((mu - torch.tensor(y)) ** 2))) < 0.35   # y spans about +-1.5
+
+
+def test_loocv_rrmse_matches_the_oracle_inverse_diagonal():
+    """loocv_rrmse (optim/mll_noise_continuation.py:28-42): rms of alpha_i / (K_y^-1)_ii, with alpha and diag(K_y^-1)
+    fetched from the device (gpp_fetch which = 3 / 4) against the oracle's dense inverse."""
+    from gpplus_b200.optim.mll_noise_continuation import loocv_rrmse
+    from gpplus_b200.optim.mll_scipy import MLLObjective
+    from oracle import gp_oracle as O
+    for builder in (_c1, _c3):
+        m, spec, _, _ = builder()
+        obj = MLLObjective(m, True, [0, 0])
+        obj._load((obj.pack_parameters() + 0.1).astype(np.float32).astype(np.float64))
+        got = loocv_rrmse(m)
+        eng = m._get_engine()
+        x = m.train_inputs[0]
+        cols = m._quant_columns()
+        with torch.no_grad():
+            w, zt, sf2, noise, beta = m._natural()
+        n_mean, _ = m._mean_layout()
+        prob = {"n": x.shape[0], "dq": len(cols), "dz": eng.dz, "n_combo": eng.n_combo, "n_noise": eng.n_noise,
+                "n_mean": n_mean, "kernel": eng.kernel, "xq": x[:, cols].double().numpy(),
+                "y": m.train_targets.double().numpy(), "level_idx": m._level_index(x, True),
+                "noise_idx": m._noise_index(x), "mean_idx": m._mean_index(x)}
+        hyp = {"w": w.double().numpy(), "z": zt.double().numpy() if eng.dz > 0 else None, "sigma_f2": float(sf2),
+               "noise": noise.double().numpy(), "beta": beta.double().numpy() if n_mean > 0 else None}
+        ref = O.mll(prob, hyp, want_grad=False, return_mats=True)
+        want = float(np.sqrt(np.mean((ref["alpha"] / np.diag(ref["Kinv"])) ** 2)))
+        assert abs(got - want) <= 1e-8 * abs(want), (got, want)
+        np.testing.assert_allclose(eng.fetch("Kinv_diag"), np.diag(ref["Kinv"]), rtol=1e-8)
+        m.release_engine()
+
+
+def test_sobol_indices_match_the_same_design_on_oracle_predictions():
+    """GP_Plus.Sobol (models/gp_plus.py:1148-1224): Saltelli estimators on engine predictions equal the same
+    estimators evaluated on the CPU oracle's predictive mean over the same A / B / AB_i design."""
+    from scipy.stats.qmc import Sobol as _Sobol
+    from oracle import gp_oracle as O
+    import warnings
+    m, spec, _, _ = _c1()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        S, ST = m.Sobol(N=512)
+    eng = m._get_engine()
+    x = m.train_inputs[0].double()
+    p = x.shape[1]
+    seq = torch.from_numpy(_Sobol(d=2 * p, scramble=False).random(513)[1:])
+    mins, maxs = x.min(dim=0)[0], x.max(dim=0)[0]
+    A = mins + (maxs - mins) * seq[:, p:]
+    B = mins + (maxs - mins) * seq[:, :p]
+    with torch.no_grad():
+        w, zt, sf2, noise, beta = m._natural()
+    prob = {"n": x.shape[0], "dq": p, "dz": 0, "n_combo": 0, "n_noise": 1, "n_mean": 1, "kernel": eng.kernel,
+            "xq": x.numpy(), "y": m.train_targets.double().numpy(), "level_idx": None, "noise_idx": None,
+            "mean_idx": None}
+    hyp = {"w": w.double().numpy(), "z": None, "sigma_f2": float(sf2), "noise": noise.double().numpy(),
+           "beta": beta.double().numpy()}
+
+    def f(X):
+        mu, _ = O.predict(prob, hyp, {"m": X.shape[0], "xq": X.numpy(), "level_idx": None, "noise_idx": None,
+                                     "mean_idx": None})
+        return (float(m.y_min) + float(m.y_std) * mu).reshape(-1, 1)
+
+    FA, FB = f(A), f(B)
+    S_ref, ST_ref = np.zeros(p), np.zeros(p)
+    for i in range(p):
+        ABi = A.clone()
+        ABi[:, i] = B[:, i]
+        Fi = f(ABi)
+        S_ref[i] = np.sum(FB * (Fi - FA)) / 512
+        ST_ref[i] = np.sum((FA - Fi) ** 2) / (2 * 512)
+    varY = np.var(np.concatenate([FA, FB]))
+    np.testing.assert_allclose(S.reshape(-1), S_ref / varY, rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(ST.reshape(-1), ST_ref / varY, rtol=1e-6, atol=1e-10)
+    m.release_engine()

@@ -7,9 +7,9 @@ import bench
 from gpplus_b200 import _engine as E
 
 for n in (32768, 49152):
-    X, y = bench.make_workload(n)
+    X, y = bench.W.c4_workload(n)
     ys = (y - y.min()) / (y.max() - y.min())
-    h = bench.natural_from_theta(0.05 * np.random.RandomState(3).randn(13))
+    h = bench.W.c4_natural(0.05 * np.random.RandomState(3).randn(13))
     res = {}
     for mode in ("lookahead", "blocked"):
         os.environ["GPP_CHOL"] = mode

@@ -5,9 +5,9 @@ import numpy as np, torch
 import bench
 from gpplus_b200 import _engine as E
 for n, m in ((8192, 65536), (2048, 262144), (512, 1048576)):
-    X, y = bench.make_workload(n)
+    X, y = bench.W.c4_workload(n)
     ys = (y - y.min()) / (y.max() - y.min())
-    h = bench.natural_from_theta(np.zeros(13))
+    h = bench.W.c4_natural(np.zeros(13))
     eng = E.Engine(xq=X, y=ys, kernel=E.KERNEL_MATERN52, n_noise=1, n_mean=1, device=0)
     eng.factorize(h)
     Xc = np.random.RandomState(0).randn(m, 10)
