@@ -16,7 +16,7 @@
 //      level h combines aligned groups of h blocks:  M21 = -M22 * (L21 * M11); every group of
 //      a level is independent, so a level is two batched GEMM launches (ceil(log2 T) levels).  The part that
 //      only needs the leading tile columns of L starts behind the factorisation on a third stream.
-//   3. lauum: K^-1 = M^T M, one launch over the lower tiles, mirrored into the upper triangle.
+//   3. lauum: K^-1 = M^T M, one launch over the lower tiles (the upper triangle is not stored on the hot path).
 #pragma once
 #include <vector>
 
@@ -832,8 +832,10 @@ inline cudaError_t trtri_late(const double* L, double* M, double* X, int ld, int
     return trtri_level(L, M, X, ld, T, H, 0, 1, 2, st);
 }
 
-// Kinv = M^T M (full symmetric storage); M lower: k-blocks [ti, T)
-inline cudaError_t lauum_full(const double* M, double* Kinv, int ld, int T, cudaStream_t st) {
+// Kinv = M^T M over the lower tiles; M lower: k-blocks [ti, T).  The hot path reads lower tiles only (the gradient
+// pass and the noise-gradient diagonal), so the upper triangle is not written unless `mirror` is set: the mirrored
+// store was 3.6x the algorithmic DRAM traffic of this launch (strided 8-byte stores, profiles/dgemm_traffic.json).
+inline cudaError_t lauum_full(const double* M, double* Kinv, int ld, int T, cudaStream_t st, int mirror = 0) {
     GemmOp op = gemm_default();
     op.A = M;
     op.lda = ld;
@@ -848,7 +850,7 @@ inline cudaError_t lauum_full(const double* M, double* Kinv, int ld, int T, cuda
     op.klo_c = 0;
     op.khi_sel = KSEL_CONST;
     op.khi_c = T;
-    op.mirror = 1;
+    op.mirror = mirror;
     return launch_gemm(op, false, false, 1, st);
 }
 

@@ -13,6 +13,7 @@
 // the rest (clamp, exp / Matern polynomial, latent RBF factor, noise) stays in registers.
 #pragma once
 #include "dgemm_dmma.cuh"
+#include "fastmath.cuh"
 #include "tma.cuh"
 
 namespace gpp {
@@ -36,18 +37,18 @@ inline __host__ __device__ int pad_dq(int dq) {
 template <int KIND>
 __device__ __forceinline__ void kq_eval(double s, double& f, double& fp) {
     if (KIND == KERNEL_EXPSQ) {
-        f = exp(-s);
+        f = exp_nonpos(-s);
         fp = -f;
     } else if (KIND == KERNEL_MATERN32) {
         const double c = 1.7320508075688772;
         double r = sqrt(s);
-        double e = exp(-c * r);
+        double e = exp_nonpos(-c * r);
         f = (1.0 + c * r) * e;
         fp = -1.5 * e;
     } else {
         const double c = 2.23606797749979;
         double r = sqrt(s);
-        double e = exp(-c * r);
+        double e = exp_nonpos(-c * r);
         f = ((c * r + 1.0) + (5.0 / 3.0) * s) * e;
         fp = -(5.0 / 6.0) * (1.0 + c * r) * e;
     }
@@ -164,10 +165,10 @@ __device__ __forceinline__ void tile_cross_dmma(const double* Xi, const double* 
     }
 }
 
-template <int KIND>
+template <int KIND, bool HAS_Z>
 __global__ void __launch_bounds__(COV_THREADS, 1) cov_tile_kernel(const CovArgs a) {
     extern __shared__ __align__(128) unsigned char smraw[];
-    const int dqp = a.dqp, dz = a.dz;
+    const int dqp = a.dqp, dz = HAS_Z ? a.dz : 0;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smraw);
     double* Xi = reinterpret_cast<double*>(smraw + 128);
     double* Xj = Xi + CT * dqp;
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(COV_THREADS, 1) cov_tile_kernel(const CovArgs 
         const double nri = sni[row];
         double zr[ZP];
 #pragma unroll
-        for (int k = 0; k < ZP; k++) zr[k] = (k < dz) ? zi[row * ZP + k] : 0.0;
+        for (int k = 0; k < ZP; k++) zr[k] = (HAS_Z && k < dz) ? zi[row * ZP + k] : 0.0;
         double msum = 0.0;
 #pragma unroll
         for (int ni = 0; ni < 4; ni++) {
@@ -236,20 +237,23 @@ __global__ void __launch_bounds__(COV_THREADS, 1) cov_tile_kernel(const CovArgs 
                 const bool on_diag = diag_tile && (row == col);
                 if (on_diag) s = 0.0;
                 double sz = 0.0;
+                if (HAS_Z) {
 #pragma unroll
-                for (int k = 0; k < ZP; k++) {
-                    if (k < dz) {
-                        double dd = zr[k] - zj[col * ZP + k];
-                        sz = fma(dd, dd, sz);
+                    for (int k = 0; k < ZP; k++) {
+                        if (k < dz) {
+                            double dd = zr[k] - zj[col * ZP + k];
+                            sz = fma(dd, dd, sz);
+                        }
                     }
                 }
                 double kval;
                 if (KIND == KERNEL_EXPSQ) {
-                    kval = sf2 * exp(-(s + 0.5 * sz));
+                    kval = sf2 * exp_nonpos(-(s + 0.5 * sz));
                 } else {
                     double f, fp;
                     kq_eval<KIND>(s, f, fp);
-                    kval = sf2 * f * (dz > 0 ? exp(-0.5 * sz) : 1.0);
+                    kval = sf2 * f;
+                    if (HAS_Z) kval *= exp_nonpos(-0.5 * sz);
                 }
                 if (on_diag && a.diag_add) kval += a.diag_add[gi < a.n_r ? gi : 0];
                 if (gi >= a.n_r || gj >= a.n_c) kval = (a.pad_identity && on_diag) ? 1.0 : 0.0;
@@ -281,7 +285,7 @@ __global__ void __launch_bounds__(COV_THREADS, 1) cov_tile_kernel(const CovArgs 
 struct GradArgs {
     const double *xs, *nrm, *zpt;  // training points
     const double* alpha;           // [np]
-    const double* Kinv;            // [np*ld] full symmetric
+    const double* Kinv;            // [np*ld] lower tiles of K_y^-1 (the upper triangle is never read)
     long long ld;
     int n, np, T;
     int dq, dqp, dz;
@@ -380,17 +384,17 @@ __global__ void __launch_bounds__(COV_THREADS, 1) grad_tile_kernel(const GradArg
                 double sz = 0.0;
 #pragma unroll
                 for (int k = 0; k < ZP; k++) {
-                    dzk[k] = (k < dz) ? (zi[row * ZP + k] - zj[col * ZP + k]) : 0.0;
-                    sz = fma(dzk[k], dzk[k], sz);
+                    dzk[k] = (HAS_Z && k < dz) ? (zi[row * ZP + k] - zj[col * ZP + k]) : 0.0;
+                    if (HAS_Z) sz = fma(dzk[k], dzk[k], sz);
                 }
                 double f, fp;
                 if (KIND == KERNEL_EXPSQ) {
-                    f = exp(-(s + 0.5 * sz));
+                    f = exp_nonpos(-(s + 0.5 * sz));
                     fp = -f;
                 } else {
                     kq_eval<KIND>(s, f, fp);
-                    if (dz > 0) {
-                        double kz = exp(-0.5 * sz);
+                    if (HAS_Z) {
+                        double kz = exp_nonpos(-0.5 * sz);
                         f *= kz;
                         fp *= kz;
                     }
@@ -585,9 +589,12 @@ inline cudaError_t cov_set_attributes() {
 #define GPP_SET(k)                                                                    \
     e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb); \
     if (e != cudaSuccess) return e;
-    GPP_SET(cov_tile_kernel<KERNEL_EXPSQ>)
-    GPP_SET(cov_tile_kernel<KERNEL_MATERN32>)
-    GPP_SET(cov_tile_kernel<KERNEL_MATERN52>)
+    GPP_SET((cov_tile_kernel<KERNEL_EXPSQ, true>))
+    GPP_SET((cov_tile_kernel<KERNEL_MATERN32, true>))
+    GPP_SET((cov_tile_kernel<KERNEL_MATERN52, true>))
+    GPP_SET((cov_tile_kernel<KERNEL_EXPSQ, false>))
+    GPP_SET((cov_tile_kernel<KERNEL_MATERN32, false>))
+    GPP_SET((cov_tile_kernel<KERNEL_MATERN52, false>))
     GPP_SET((grad_tile_kernel<KERNEL_EXPSQ, true>))
     GPP_SET((grad_tile_kernel<KERNEL_MATERN32, true>))
     GPP_SET((grad_tile_kernel<KERNEL_MATERN52, true>))
@@ -603,9 +610,15 @@ inline cudaError_t launch_cov(const CovArgs& a, int kind, cudaStream_t st) {
     if (nt <= 0) return cudaSuccess;
     size_t sm = cov_smem_bytes(a.dqp);
     count_launch();
-    if (kind == KERNEL_EXPSQ) cov_tile_kernel<KERNEL_EXPSQ><<<nt, COV_THREADS, sm, st>>>(a);
-    else if (kind == KERNEL_MATERN32) cov_tile_kernel<KERNEL_MATERN32><<<nt, COV_THREADS, sm, st>>>(a);
-    else cov_tile_kernel<KERNEL_MATERN52><<<nt, COV_THREADS, sm, st>>>(a);
+    if (a.dz > 0) {
+        if (kind == KERNEL_EXPSQ) cov_tile_kernel<KERNEL_EXPSQ, true><<<nt, COV_THREADS, sm, st>>>(a);
+        else if (kind == KERNEL_MATERN32) cov_tile_kernel<KERNEL_MATERN32, true><<<nt, COV_THREADS, sm, st>>>(a);
+        else cov_tile_kernel<KERNEL_MATERN52, true><<<nt, COV_THREADS, sm, st>>>(a);
+    } else {
+        if (kind == KERNEL_EXPSQ) cov_tile_kernel<KERNEL_EXPSQ, false><<<nt, COV_THREADS, sm, st>>>(a);
+        else if (kind == KERNEL_MATERN32) cov_tile_kernel<KERNEL_MATERN32, false><<<nt, COV_THREADS, sm, st>>>(a);
+        else cov_tile_kernel<KERNEL_MATERN52, false><<<nt, COV_THREADS, sm, st>>>(a);
+    }
     return cudaGetLastError();
 }
 
