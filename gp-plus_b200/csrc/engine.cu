@@ -97,6 +97,8 @@ struct gpp_handle {
     bool use_graph = false;
     bool early_out = true;   // read the factorisation status before enqueueing the rest (non-graph path)
     bool capturing = false;
+    bool pending = false;    // gpp_objective_enqueue issued, gpp_objective_collect not yet called
+    int pending_grad = 0;
     gpp_stats stats;
     cudaEvent_t ev_info = nullptr;                 // factorisation status available (jitter-ladder early-out)
     ThetaLayout layout;                            // optional: O(p) host side of MLLObjective.fun
@@ -111,7 +113,7 @@ static const double* hyp_beta(const gpp_handle* h) { return h->hyp + h->dq + h->
 static const double* hyp_sf2(const gpp_handle* h) { return hyp_beta(h) + h->n_mean; }
 static const double* hyp_jitter(const gpp_handle* h) { return hyp_beta(h) + h->n_mean + 1; }
 
-extern "C" int gpp_version(void) { return 102; }
+extern "C" int gpp_version(void) { return 103; }
 
 extern "C" int gpp_device_count(void) {
     int c = 0;
@@ -580,9 +582,9 @@ static int enqueue_eval_early_out(gpp_handle* h, int want_grad, int* failed) {
 }
 
 // one evaluation with the jitter ladder; on success L is in A, L^-1 in M, alpha / res_host are valid
-static int run_eval(gpp_handle* h, const gpp_hyper* hy, int want_grad) {
-    h->stats.evaluations++;
-    for (int a = 0; a < 4; a++) {
+static int run_eval(gpp_handle* h, const gpp_hyper* hy, int want_grad, int first_rung = 0) {
+    if (first_rung == 0) h->stats.evaluations++;
+    for (int a = first_rung; a < 4; a++) {
         for (int i = 0; i < EV_COUNT; i++) h->ev_valid[i] = false;
         fill_hyper_host(h, hy, kJitter[a]);
         if (h->use_graph && !ensure_graph(h, want_grad)) h->use_graph = false;
@@ -623,16 +625,8 @@ static int run_eval(gpp_handle* h, const gpp_hyper* hy, int want_grad) {
     return GPP_ERR_NOT_PD;
 }
 
-extern "C" int gpp_mll_grad(gpp_handle* h, const gpp_hyper* hy, int want_grad, gpp_mll_result* out) {
-    if (!h || !out) ARG_FAIL("gpp_mll_grad: null argument");
-    int rc = check_hyper(h, hy);
-    if (rc != GPP_OK) return rc;
-    CK(cudaSetDevice(h->device));
-    h->factorized = false;
-    rc = run_eval(h, hy, want_grad ? 1 : 0);
-    if (rc != GPP_OK) return rc;
-    h->factorized = true;
-
+// results of the evaluation that just completed on h->st (res_host / gz_host are valid) into `out`
+static int collect_mll(gpp_handle* h, int want_grad, gpp_mll_result* out) {
     const double* r = h->res_host;
     out->quad = r[0];
     out->logdet = r[1];
@@ -672,6 +666,19 @@ extern "C" int gpp_mll_grad(gpp_handle* h, const gpp_hyper* hy, int want_grad, g
     return GPP_OK;
 }
 
+extern "C" int gpp_mll_grad(gpp_handle* h, const gpp_hyper* hy, int want_grad, gpp_mll_result* out) {
+    if (!h || !out) ARG_FAIL("gpp_mll_grad: null argument");
+    int rc = check_hyper(h, hy);
+    if (rc != GPP_OK) return rc;
+    CK(cudaSetDevice(h->device));
+    h->factorized = false;
+    h->pending = false;
+    rc = run_eval(h, hy, want_grad ? 1 : 0);
+    if (rc != GPP_OK) return rc;
+    h->factorized = true;
+    return collect_mll(h, want_grad, out);
+}
+
 extern "C" int gpp_set_theta_layout(gpp_handle* h, const gpp_theta_layout* layout) {
     if (!h || !layout) ARG_FAIL("gpp_set_theta_layout: null argument");
     const char* err = layout_copy(h->layout, layout, h->dq, h->dz, h->n_combo, h->n_noise, h->n_mean);
@@ -686,26 +693,27 @@ extern "C" int gpp_set_theta_layout(gpp_handle* h, const gpp_theta_layout* layou
     return GPP_OK;
 }
 
-extern "C" int gpp_objective(gpp_handle* h, const double* theta, int want_grad, double* value, double* grad,
-                             gpp_mll_result* detail) {
-    if (!h || !theta || !value) ARG_FAIL("gpp_objective: null argument");
-    if (!h->layout.set) ARG_FAIL("gpp_objective: call gpp_set_theta_layout first");
-    if (want_grad && !grad) ARG_FAIL("gpp_objective: grad missing");
+static gpp_hyper layout_hyper(gpp_handle* h) {
     ThetaLayout& L = h->layout;
-    layout_natural(L, theta, h->dq, h->dz, h->n_combo, h->n_noise, h->n_mean);
     gpp_hyper hy;
     hy.w = L.w.data();
     hy.z = h->dz > 0 ? L.z.data() : nullptr;
     hy.sigma_f2 = L.sf2;
     hy.noise = L.noise.data();
     hy.beta = h->n_mean > 0 ? L.beta.data() : nullptr;
+    return hy;
+}
+
+// chain rule to the raw parameters + log-priors on top of a finished evaluation
+static int finish_objective(gpp_handle* h, int want_grad, double* value, double* grad, gpp_mll_result* detail) {
+    ThetaLayout& L = h->layout;
     gpp_mll_result r;
     memset(&r, 0, sizeof(r));
     r.d_w = h->g_w.data();
     r.d_z = h->g_z.data();
     r.d_noise = h->g_noise.data();
     r.d_beta = h->g_beta.data();
-    int rc = gpp_mll_grad(h, &hy, want_grad, &r);
+    int rc = collect_mll(h, want_grad, &r);
     if (rc != GPP_OK) return rc;
     if (want_grad) layout_chain(L, r, h->dq, h->dz, h->n_combo, h->n_noise, h->n_mean, grad);
     const double logp = layout_priors(L, want_grad ? grad : nullptr);
@@ -722,6 +730,76 @@ extern "C" int gpp_objective(gpp_handle* h, const double* theta, int want_grad, 
         return GPP_ERR_NAN;
     }
     return GPP_OK;
+}
+
+extern "C" int gpp_objective(gpp_handle* h, const double* theta, int want_grad, double* value, double* grad,
+                             gpp_mll_result* detail) {
+    if (!h || !theta || !value) ARG_FAIL("gpp_objective: null argument");
+    if (!h->layout.set) ARG_FAIL("gpp_objective: call gpp_set_theta_layout first");
+    if (want_grad && !grad) ARG_FAIL("gpp_objective: grad missing");
+    layout_natural(h->layout, theta, h->dq, h->dz, h->n_combo, h->n_noise, h->n_mean);
+    gpp_hyper hy = layout_hyper(h);
+    CK(cudaSetDevice(h->device));
+    h->factorized = false;
+    h->pending = false;
+    int rc = run_eval(h, &hy, want_grad ? 1 : 0);
+    if (rc != GPP_OK) return rc;
+    h->factorized = true;
+    return finish_objective(h, want_grad, value, grad, detail);
+}
+
+// Split form of gpp_objective for callers that keep MANY handles in flight from one host thread (the lock-step
+// multi-start driver of fit_model_scipy): enqueue issues the whole evaluation on the handle's stream and returns
+// without waiting; collect waits for it, walks the rest of the jitter ladder if the first factorisation failed, and
+// applies the chain rule and the priors.  Values are identical to gpp_objective.
+extern "C" int gpp_objective_enqueue(gpp_handle* h, const double* theta, int want_grad) {
+    if (!h || !theta) ARG_FAIL("gpp_objective_enqueue: null argument");
+    if (!h->layout.set) ARG_FAIL("gpp_objective_enqueue: call gpp_set_theta_layout first");
+    if (h->pending) ARG_FAIL("gpp_objective_enqueue: the previous evaluation has not been collected");
+    layout_natural(h->layout, theta, h->dq, h->dz, h->n_combo, h->n_noise, h->n_mean);
+    gpp_hyper hy = layout_hyper(h);
+    CK(cudaSetDevice(h->device));
+    h->factorized = false;
+    h->stats.evaluations++;
+    h->stats.factorizations++;
+    const int wg = want_grad ? 1 : 0;
+    for (int i = 0; i < EV_COUNT; i++) h->ev_valid[i] = false;
+    fill_hyper_host(h, &hy, kJitter[0]);
+    if (h->use_graph && !ensure_graph(h, wg)) h->use_graph = false;
+    if (h->use_graph) {
+        CK(cudaGraphLaunch(h->graph_exec[wg], h->st));
+        count_launch((int)h->graph_kernels[wg]);
+    } else {
+        int rc = enqueue_eval(h, wg);
+        if (rc != GPP_OK) return rc;
+    }
+    h->pending = true;
+    h->pending_grad = wg;
+    return GPP_OK;
+}
+
+extern "C" int gpp_objective_collect(gpp_handle* h, double* value, double* grad, gpp_mll_result* detail) {
+    if (!h || !value) ARG_FAIL("gpp_objective_collect: null argument");
+    if (!h->pending) ARG_FAIL("gpp_objective_collect: nothing was enqueued");
+    const int wg = h->pending_grad;
+    if (wg && !grad) ARG_FAIL("gpp_objective_collect: grad missing");
+    CK(cudaSetDevice(h->device));
+    h->pending = false;
+    CK(cudaStreamSynchronize(h->st));
+    const int info = (int)h->res_host[2];
+    if (info & 2) {
+        g_err = "NaN encountered while factorising K_y";
+        return GPP_ERR_NAN;
+    }
+    if (info != 0) {
+        gpp_hyper hy = layout_hyper(h);  // the natural parameters of the enqueued theta are still in the layout
+        int rc = run_eval(h, &hy, wg, 1);
+        if (rc != GPP_OK) return rc;
+    } else {
+        h->last_jitter = kJitter[0];
+    }
+    h->factorized = true;
+    return finish_objective(h, wg, value, grad, detail);
 }
 
 extern "C" int gpp_get_timings(gpp_handle* h, gpp_timings* out) {

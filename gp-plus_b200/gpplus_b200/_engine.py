@@ -22,7 +22,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libg
 EXPORTS = (
     "gpp_version", "gpp_device_count", "gpp_last_error", "gpp_launch_count", "gpp_create", "gpp_destroy", "gpp_mll_grad",
     "gpp_get_timings", "gpp_get_stats", "gpp_covariance", "gpp_fetch", "gpp_factorize", "gpp_predict", "gpp_acq_argmax",
-    "gpp_probe_dgemm", "gpp_set_theta_layout", "gpp_objective",
+    "gpp_probe_dgemm", "gpp_set_theta_layout", "gpp_objective", "gpp_objective_enqueue", "gpp_objective_collect",
 )
 
 PRIOR_NORMAL, PRIOR_LOGNORMAL_OS, PRIOR_HORSESHOE, PRIOR_MOLLIFIED, PRIOR_CONST = 0, 1, 2, 3, 4
@@ -129,6 +129,10 @@ def load_library():
         lib.gpp_set_theta_layout.restype = C.c_int
         lib.gpp_objective.argtypes = [C.c_void_p, C.c_void_p, C.c_int, _dp, C.c_void_p, C.POINTER(_MllResult)]
         lib.gpp_objective.restype = C.c_int
+        lib.gpp_objective_enqueue.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        lib.gpp_objective_enqueue.restype = C.c_int
+        lib.gpp_objective_collect.argtypes = [C.c_void_p, _dp, C.c_void_p, C.POINTER(_MllResult)]
+        lib.gpp_objective_collect.restype = C.c_int
         _lib = lib
         return lib
 
@@ -324,6 +328,25 @@ class Engine:
             _raise(rc, "gpp_objective")
         if want_grad:
             return self._val_buf.value, grad
+        return self._val_buf.value
+
+    def objective_enqueue(self, theta, want_grad: bool = True):
+        """Issue ``objective(theta)`` on this handle's stream without waiting (pair with ``objective_collect``)."""
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        if th.shape[0] != self._p:
+            raise ValueError("theta must have %d entries" % self._p)
+        self._pending_theta = th  # keep the buffer alive until the call returns (it is copied inside)
+        rc = self._lib.gpp_objective_enqueue(self._h, th.ctypes.data, 1 if want_grad else 0)
+        if rc != GPP_OK:
+            _raise(rc, "gpp_objective_enqueue")
+
+    def objective_collect(self, grad_out=None):
+        """Wait for the enqueued evaluation; returns the value and writes the gradient into ``grad_out`` (length p).
+        Raises NotPSDError / NanError exactly like ``objective``."""
+        rc = self._lib.gpp_objective_collect(self._h, C.byref(self._val_buf),
+                                             grad_out.ctypes.data if grad_out is not None else None, None)
+        if rc != GPP_OK:
+            _raise(rc, "gpp_objective_collect")
         return self._val_buf.value
 
     def timings(self) -> Dict[str, float]:

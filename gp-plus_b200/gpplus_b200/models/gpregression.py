@@ -193,12 +193,9 @@ class GPR(Module):
     def _mean_index(self, x: torch.Tensor) -> Optional[np.ndarray]:
         return None
 
-    def _get_engine(self) -> "_engine.Engine":
-        dev = get_default_device()
-        if self._engine is not None and self._engine_device == dev:
-            return self._engine
-        if self._engine is not None:
-            self._engine.close()
+    def _new_engine(self, dev: int) -> "_engine.Engine":
+        """A fresh engine handle holding this model's training set on GPU ``dev`` (not cached: the lock-step
+        multi-start driver keeps one handle per in-flight restart)."""
         x = self.train_inputs[0]
         qk = self._quant_kernel() if len(self._quant_columns()) > 0 else None
         family = qk.family if qk is not None else _engine.KERNEL_EXPSQ
@@ -206,11 +203,19 @@ class GPR(Module):
         n_mean, _ = self._mean_layout()
         n_noise = int(self.likelihood.noise_covar.raw_noise.numel())
         xq = x[:, self._quant_columns()].detach().double().cpu().numpy() if qk is not None else None
-        self._engine = _engine.Engine(
+        return _engine.Engine(
             xq=xq, y=self.train_targets.detach().double().cpu().numpy(), kernel=family,
             level_idx=self._level_index(x, True), n_combo=0 if table is None else int(table.shape[0]),
             dz=0 if table is None else int(table.shape[1]), noise_idx=self._noise_index(x), n_noise=n_noise,
             mean_idx=self._mean_index(x), n_mean=n_mean, device=dev)
+
+    def _get_engine(self) -> "_engine.Engine":
+        dev = get_default_device()
+        if self._engine is not None and self._engine_device == dev:
+            return self._engine
+        if self._engine is not None:
+            self._engine.close()
+        self._engine = self._new_engine(dev)
         self._engine_device = dev
         self._factor_key = None
         return self._engine

@@ -281,6 +281,49 @@ def _run_restarts(likobj, theta0_list, work, jac, options, method, constraint, b
     return results
 
 
+def _use_lockstep(likobj, method, jac, constraint) -> bool:
+    """Small problems (CUDA-graph replay, N <= 2048) with the native objective layout: one host thread per GPU keeps
+    up to 64 L-BFGS-B restarts in flight (optim/_lockstep.py) instead of one host thread per restart."""
+    if os.environ.get("GPPLUS_LOCKSTEP", "1") == "0":
+        return False
+    if method != "L-BFGS-B" or jac is not True or constraint is True:
+        return False
+    if getattr(likobj, "_fast", None) is None or not likobj._native:
+        return False
+    return int(likobj.model.train_targets.shape[0]) <= 2048
+
+
+def _run_restarts_lockstep(likobj, theta0_list, work, options, bounds) -> Dict[int, object]:
+    from . import _lockstep
+    lo = hi = None
+    if bounds is True and len(theta0_list) > 0:
+        lo, hi = get_bounds(likobj, theta0_list[0])
+    devices = parallel.local_devices()
+    if len(devices) == 1 or work.count <= 1:
+        return _lockstep.run_lockstep(likobj, theta0_list, work, options, lo, hi, devices[0])
+    results: Dict[int, object] = {}
+    errors: List[BaseException] = []
+    lock = threading.Lock()
+
+    def drive(dev):
+        try:
+            out = _lockstep.run_lockstep(likobj, theta0_list, work, options, lo, hi, dev)
+            with lock:
+                results.update(out)
+        except BaseException as e:
+            with lock:
+                errors.append(e)
+
+    threads = [threading.Thread(target=drive, args=(d,), daemon=True) for d in devices]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return results
+
+
 def fit_model_scipy(
     model,
     add_prior: bool = True,
@@ -316,7 +359,10 @@ def fit_model_scipy(
 
     # restarts are claimed from a cross-rank work queue (the reference: joblib's dynamic dispatch, :287-293)
     work = parallel.RestartQueue(len(theta0_list))
-    local = _run_restarts(likobj, theta0_list, work, jac, defaults, method, constraint, bounds, n_jobs)
+    if _use_lockstep(likobj, method, jac, constraint):
+        local = _run_restarts_lockstep(likobj, theta0_list, work, defaults, bounds)
+    else:
+        local = _run_restarts(likobj, theta0_list, work, jac, defaults, method, constraint, bounds, n_jobs)
     out = parallel.gather_restarts(local, len(theta0_list), len(theta0_list[0]) if theta0_list else 0)
 
     nlls_opt = [np.inf if isinstance(res, Exception) else res.fun for res in out]

@@ -215,6 +215,14 @@ int gpp_set_theta_layout(gpp_handle* h, const gpp_theta_layout* layout);
 int gpp_objective(gpp_handle* h, const double* theta, int want_grad, double* value, double* grad,
                   gpp_mll_result* detail);
 
+/* Split form for callers that keep many handles in flight from ONE host thread (the lock-step multi-start driver
+ * behind fit_model_scipy, optim/mll_scipy.py:287-293 of the reference fans restarts out over processes):
+ * gpp_objective_enqueue issues the evaluation on the handle's stream and returns without waiting;
+ * gpp_objective_collect waits for it, walks the rest of the jitter ladder if needed, and returns exactly what
+ * gpp_objective would have returned (want_grad as given to enqueue). */
+int gpp_objective_enqueue(gpp_handle* h, const double* theta, int want_grad);
+int gpp_objective_collect(gpp_handle* h, double* value, double* grad, gpp_mll_result* detail);
+
 /* FP64 DMMA GEMM probe used by bench/selftest: C[m x n] = A[m x k] * B[n x k]^T on device
  * scratch, returns average milliseconds per launch over iters (m,n,k multiples of 128). */
 int gpp_probe_dgemm(int device, int m, int n, int k, int iters, float* ms_out);

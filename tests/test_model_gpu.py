@@ -425,3 +425,58 @@ def test_sobol_indices_match_the_same_design_on_oracle_predictions():
     np.testing.assert_allclose(S.reshape(-1), S_ref / varY, rtol=1e-6, atol=1e-8)
     np.testing.assert_allclose(ST.reshape(-1), ST_ref / varY, rtol=1e-6, atol=1e-10)
     m.release_engine()
+
+
+def test_split_objective_equals_the_blocking_call_bitwise():
+    """gpp_objective_enqueue + gpp_objective_collect on several handles in flight == gpp_objective, bit for bit."""
+    from gpplus_b200.optim.mll_scipy import MLLObjective, _sample_from_prior
+    m, spec, _, _ = _c2()
+    obj = MLLObjective(m, True, [0, 0])
+    assert obj.enable_fast_path()
+    layout = obj._fast.layout_spec()
+    torch.manual_seed(5)
+    thetas = [np.clip(_sample_from_prior(m), -5, 3) for _ in range(6)]
+    ref = m._new_engine(0)
+    ref.set_theta_layout(layout)
+    want = [ref.objective(t, True) for t in thetas]
+    engines = [m._new_engine(0) for _ in thetas]
+    try:
+        for e in engines:
+            e.set_theta_layout(layout)
+        for rep in range(2):
+            for e, t in zip(engines, thetas):
+                e.objective_enqueue(t, True)
+            for e, (f, g) in zip(engines, want):
+                grad = np.empty_like(g)
+                val = e.objective_collect(grad)
+                assert val == f and np.array_equal(grad, g)
+        with pytest.raises(ValueError):
+            engines[0].objective_collect(np.empty_like(want[0][1]))  # nothing enqueued
+    finally:
+        for e in engines + [ref]:
+            e.close()
+    m.release_engine()
+
+
+def test_lockstep_driver_reproduces_the_threaded_fit_restart_by_restart(monkeypatch):
+    """The single-thread lock-step driver (optim/_lockstep.py) and the one-thread-per-restart path run the same
+    scipy L-BFGS-B state machines on the same objective: every restart ends at the same point after the same
+    number of iterations and evaluations."""
+    from gpplus_b200.optim.mll_scipy import _sample_from_prior, fit_model_scipy
+    m, spec, Xte, yte = _c2()
+    torch.manual_seed(11)
+    starts = [_sample_from_prior(m) for _ in range(10)]
+    monkeypatch.setenv("GPPLUS_LOCKSTEP", "0")
+    out_t, best_t = fit_model_scipy(m, theta0_list=[s.copy() for s in starts], bounds=True)
+    monkeypatch.setenv("GPPLUS_LOCKSTEP", "1")
+    m2, *_ = _c2()
+    out_l, best_l = fit_model_scipy(m2, theta0_list=[s.copy() for s in starts], bounds=True)
+    assert best_l == best_t
+    for a, b in zip(out_t, out_l):
+        if isinstance(a, Exception) or isinstance(b, Exception):
+            assert type(a) is type(b)
+            continue
+        assert a.fun == b.fun and a.nit == b.nit and a.nfev == b.nfev and a.status == b.status
+        assert np.array_equal(a.x, b.x) and a.message == b.message
+    m.release_engine()
+    m2.release_engine()
