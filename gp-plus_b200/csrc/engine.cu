@@ -99,6 +99,8 @@ struct gpp_handle {
     bool capturing = false;
     bool pending = false;    // gpp_objective_enqueue issued, gpp_objective_collect not yet called
     int pending_grad = 0;
+    void* slab = nullptr;         // one device allocation holds every per-handle buffer below (gpp_create)
+    void* pinned_slab = nullptr;  // one pinned allocation holds hyp_host / info_host / res_host / gz_host
     gpp_stats stats;
     cudaEvent_t ev_info = nullptr;                 // factorisation status available (jitter-ladder early-out)
     ThetaLayout layout;                            // optional: O(p) host side of MLLObjective.fun
@@ -137,17 +139,12 @@ extern "C" void gpp_destroy(gpp_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->st) cudaStreamSynchronize(h->st);
-    void* dptrs[] = {h->xq, h->y, h->centre, h->level_idx, h->noise_idx, h->mean_idx, h->hyp, h->xs, h->nrm, h->zpt,
-                     h->r, h->diag_add, h->v, h->alpha, h->part, h->A, h->M, h->S, h->logdet_part, h->info,
-                     h->tile_part, h->zpart, h->gz, h->res, h->c_xq, h->c_xs, h->c_nrm, h->c_zpt, h->c_K, h->c_lvl,
+    void* dptrs[] = {h->slab, h->c_xq, h->c_xs, h->c_nrm, h->c_zpt, h->c_K, h->c_lvl,
                      h->c_noise, h->c_mean, h->c_cost, h->c_mean_part, h->c_rowsq, h->c_mu, h->c_var, h->c_score,
                      h->c_blk_best, h->c_blk_idx, h->acq_par, h->acq_kind};
     for (void* p : dptrs)
         if (p) cudaFree(p);
-    if (h->hyp_host) cudaFreeHost(h->hyp_host);
-    if (h->info_host) cudaFreeHost(h->info_host);
-    if (h->res_host) cudaFreeHost(h->res_host);
-    if (h->gz_host) cudaFreeHost(h->gz_host);
+    if (h->pinned_slab) cudaFreeHost(h->pinned_slab);
     for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(h->ev[i]);
     if (h->ev_info) cudaEventDestroy(h->ev_info);
     for (int i = 0; i < 2; i++)
@@ -241,85 +238,120 @@ extern "C" int gpp_create(const gpp_problem* p, int device, gpp_handle** out) {
     }
     CKH(h->la.init(h->T));
 
-    CKH(dev_alloc(&h->xq, (size_t)n * h->dq));
-    CKH(dev_alloc(&h->y, (size_t)n));
-    CKH(dev_alloc(&h->centre, (size_t)std::max(h->dq, 1)));
-    if (h->dq > 0) CKH(cudaMemcpy(h->xq, p->xq, sizeof(double) * n * h->dq, cudaMemcpyDefault));
-    CKH(cudaMemcpy(h->y, p->y, sizeof(double) * n, cudaMemcpyDefault));
-    {
-        // column means of the training inputs (the centring of gpytorch's covar_dist)
-        std::vector<double> xh((size_t)n * std::max(h->dq, 1)), c(std::max(h->dq, 1), 0.0);
-        if (h->dq > 0) CKH(cudaMemcpy(xh.data(), h->xq, sizeof(double) * n * h->dq, cudaMemcpyDeviceToHost));
-        for (int d = 0; d < h->dq; d++) {
-            double s = 0.0;
-            for (long long i = 0; i < n; i++) s += xh[i * h->dq + d];
-            c[d] = s / (double)n;
-        }
-        CKH(cudaMemcpy(h->centre, c.data(), sizeof(double) * std::max(h->dq, 1), cudaMemcpyHostToDevice));
-    }
-    auto upload_idx = [&](const int32_t* src, int** dst, int hi, const char* name) -> int {
-        if (!src) return GPP_OK;
-        std::vector<int> tmp((size_t)n);
-        cudaError_t e = cudaMemcpy(tmp.data(), src, sizeof(int) * n, cudaMemcpyDefault);
-        if (e != cudaSuccess) {
-            set_err("index upload", e);
-            return GPP_ERR_CUDA;
-        }
-        for (long long i = 0; i < n; i++)
-            if (tmp[i] >= hi || tmp[i] < -1) {
-                g_err = std::string("gpp_create: ") + name + " out of range";
-                return GPP_ERR_ARG;
-            }
-        e = dev_alloc(dst, (size_t)n);
-        if (e == cudaSuccess) e = cudaMemcpy(*dst, tmp.data(), sizeof(int) * n, cudaMemcpyHostToDevice);
-        if (e != cudaSuccess) {
-            set_err("index upload", e);
-            return GPP_ERR_CUDA;
-        }
-        if (dst == &h->level_idx) h->level_idx_host = tmp;
-        return GPP_OK;
-    };
-    int rc;
-    if (h->dz > 0 && (rc = upload_idx(p->level_idx, &h->level_idx, h->n_combo, "level_idx")) != GPP_OK) {
-        gpp_destroy(h);
-        return rc;
-    }
-    if ((rc = upload_idx(p->noise_idx, &h->noise_idx, h->n_noise, "noise_idx")) != GPP_OK) {
-        gpp_destroy(h);
-        return rc;
-    }
-    if ((rc = upload_idx(p->mean_idx, &h->mean_idx, std::max(h->n_mean, 1), "mean_idx")) != GPP_OK) {
-        gpp_destroy(h);
-        return rc;
-    }
-
     h->hyp_len = h->dq + h->n_combo * h->dz + h->n_noise + h->n_mean + 2;
-    CKH(dev_alloc(&h->hyp, (size_t)h->hyp_len));
-    CKH(cudaMallocHost((void**)&h->hyp_host, sizeof(double) * std::max(h->hyp_len, 1)));
-    CKH(dev_alloc(&h->xs, (size_t)np * h->dqp));
-    CKH(dev_alloc(&h->nrm, (size_t)np));
-    CKH(dev_alloc(&h->zpt, (size_t)np * ZP));
-    CKH(dev_alloc(&h->r, (size_t)np));
-    CKH(dev_alloc(&h->diag_add, (size_t)np));
-    CKH(dev_alloc(&h->v, (size_t)np));
-    CKH(dev_alloc(&h->alpha, (size_t)np));
-    CKH(dev_alloc(&h->part, (size_t)T * np));
-    CKH(dev_alloc(&h->A, (size_t)np * np));
-    CKH(dev_alloc(&h->M, (size_t)np * np));
-    CKH(dev_alloc(&h->S, (size_t)np * np));
-    CKH(cudaMemsetAsync(h->M, 0, sizeof(double) * np * np, h->st));
-    CKH(dev_alloc(&h->logdet_part, (size_t)T));
-    CKH(dev_alloc(&h->info, 1));
-    CKH(cudaMallocHost((void**)&h->info_host, sizeof(int)));
-    CKH(dev_alloc(&h->tile_part, (size_t)T * (T + 1) / 2 * (1 + h->dqp)));
-    if (h->dz > 0) {
-        CKH(dev_alloc(&h->zpart, (size_t)T * np * ZP));
-        CKH(dev_alloc(&h->gz, (size_t)n * h->dz));
-        CKH(cudaMallocHost((void**)&h->gz_host, sizeof(double) * n * h->dz));
-    }
     h->res_len = 4 + h->dq + h->n_noise + h->n_mean;
-    CKH(dev_alloc(&h->res, (size_t)h->res_len));
-    CKH(cudaMallocHost((void**)&h->res_host, sizeof(double) * h->res_len));
+    {
+        // ONE device allocation and ONE pinned allocation per handle: the lock-step multi-start driver creates up to
+        // 64 handles per fit, and ~45 separate cudaMalloc / cudaMallocHost calls per handle dominated its start-up
+        size_t off = 0;
+        auto take = [&](size_t bytes) {
+            size_t at = off;
+            off += (std::max<size_t>(bytes, 8) + 255) / 256 * 256;
+            return at;
+        };
+        const size_t D = sizeof(double), I = sizeof(int);
+        const size_t o_xq = take(D * n * h->dq), o_y = take(D * n), o_centre = take(D * std::max(h->dq, 1));
+        const size_t o_lvl = take(I * n), o_nidx = take(I * n), o_midx = take(I * n);
+        const size_t o_hyp = take(D * h->hyp_len), o_xs = take(D * np * h->dqp), o_nrm = take(D * np);
+        const size_t o_zpt = take(D * np * ZP), o_r = take(D * np), o_da = take(D * np), o_v = take(D * np);
+        const size_t o_alpha = take(D * np), o_part = take(D * T * np);
+        const size_t o_A = take(D * np * np), o_M = take(D * np * np), o_S = take(D * np * np);
+        const size_t o_ld = take(D * T), o_info = take(I);
+        const size_t o_tp = take(D * (size_t)T * (T + 1) / 2 * (1 + h->dqp));
+        const size_t o_zpart = take(h->dz > 0 ? D * T * np * ZP : 8), o_gz = take(h->dz > 0 ? D * n * h->dz : 8);
+        const size_t o_res = take(D * h->res_len);
+        CKH(cudaMalloc(&h->slab, off));
+        char* base = (char*)h->slab;
+        h->xq = (double*)(base + o_xq);
+        h->y = (double*)(base + o_y);
+        h->centre = (double*)(base + o_centre);
+        h->hyp = (double*)(base + o_hyp);
+        h->xs = (double*)(base + o_xs);
+        h->nrm = (double*)(base + o_nrm);
+        h->zpt = (double*)(base + o_zpt);
+        h->r = (double*)(base + o_r);
+        h->diag_add = (double*)(base + o_da);
+        h->v = (double*)(base + o_v);
+        h->alpha = (double*)(base + o_alpha);
+        h->part = (double*)(base + o_part);
+        h->A = (double*)(base + o_A);
+        h->M = (double*)(base + o_M);
+        h->S = (double*)(base + o_S);
+        h->logdet_part = (double*)(base + o_ld);
+        h->info = (int*)(base + o_info);
+        h->tile_part = (double*)(base + o_tp);
+        if (h->dz > 0) {
+            h->zpart = (double*)(base + o_zpart);
+            h->gz = (double*)(base + o_gz);
+        }
+        h->res = (double*)(base + o_res);
+        int* idx_slots[3] = {(int*)(base + o_lvl), (int*)(base + o_nidx), (int*)(base + o_midx)};
+
+        size_t poff = 0;
+        auto ptake = [&](size_t bytes) {
+            size_t at = poff;
+            poff += (std::max<size_t>(bytes, 8) + 63) / 64 * 64;
+            return at;
+        };
+        const size_t p_hyp = ptake(D * h->hyp_len), p_info = ptake(I), p_res = ptake(D * h->res_len);
+        const size_t p_gz = ptake(h->dz > 0 ? D * n * h->dz : 8);
+        CKH(cudaMallocHost(&h->pinned_slab, poff));
+        char* pb = (char*)h->pinned_slab;
+        h->hyp_host = (double*)(pb + p_hyp);
+        h->info_host = (int*)(pb + p_info);
+        h->res_host = (double*)(pb + p_res);
+        if (h->dz > 0) h->gz_host = (double*)(pb + p_gz);
+
+        if (h->dq > 0) CKH(cudaMemcpy(h->xq, p->xq, sizeof(double) * n * h->dq, cudaMemcpyDefault));
+        CKH(cudaMemcpy(h->y, p->y, sizeof(double) * n, cudaMemcpyDefault));
+        {
+            // column means of the training inputs (the centring of gpytorch's covar_dist)
+            std::vector<double> xh((size_t)n * std::max(h->dq, 1)), c(std::max(h->dq, 1), 0.0);
+            if (h->dq > 0) CKH(cudaMemcpy(xh.data(), p->xq, sizeof(double) * n * h->dq, cudaMemcpyDefault));
+            for (int d = 0; d < h->dq; d++) {
+                double sacc = 0.0;
+                for (long long i = 0; i < n; i++) sacc += xh[i * h->dq + d];
+                c[d] = sacc / (double)n;
+            }
+            CKH(cudaMemcpy(h->centre, c.data(), sizeof(double) * std::max(h->dq, 1), cudaMemcpyHostToDevice));
+        }
+        auto upload_idx = [&](const int32_t* src, int* slot, int** dst, int hi, const char* name) -> int {
+            if (!src) return GPP_OK;
+            std::vector<int> tmp((size_t)n);
+            cudaError_t e = cudaMemcpy(tmp.data(), src, sizeof(int) * n, cudaMemcpyDefault);
+            if (e != cudaSuccess) {
+                set_err("index upload", e);
+                return GPP_ERR_CUDA;
+            }
+            for (long long i = 0; i < n; i++)
+                if (tmp[i] >= hi || tmp[i] < -1) {
+                    g_err = std::string("gpp_create: ") + name + " out of range";
+                    return GPP_ERR_ARG;
+                }
+            e = cudaMemcpy(slot, tmp.data(), sizeof(int) * n, cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) {
+                set_err("index upload", e);
+                return GPP_ERR_CUDA;
+            }
+            *dst = slot;
+            if (dst == &h->level_idx) h->level_idx_host = tmp;
+            return GPP_OK;
+        };
+        int rc;
+        if (h->dz > 0 && (rc = upload_idx(p->level_idx, idx_slots[0], &h->level_idx, h->n_combo, "level_idx")) != GPP_OK) {
+            gpp_destroy(h);
+            return rc;
+        }
+        if ((rc = upload_idx(p->noise_idx, idx_slots[1], &h->noise_idx, h->n_noise, "noise_idx")) != GPP_OK) {
+            gpp_destroy(h);
+            return rc;
+        }
+        if ((rc = upload_idx(p->mean_idx, idx_slots[2], &h->mean_idx, std::max(h->n_mean, 1), "mean_idx")) != GPP_OK) {
+            gpp_destroy(h);
+            return rc;
+        }
+    }
+    CKH(cudaMemsetAsync(h->M, 0, sizeof(double) * np * np, h->st));
     CKH(cudaStreamSynchronize(h->st));
 #undef CKH
     *out = h;

@@ -70,6 +70,9 @@ class _Chain:
         self.dsave = np.zeros(29, dtype=np.float64)
         self.nit = 0
         self.nfev = 0
+        self._x_eval = None   # last point evaluated (scipy's ScalarFunction does not re-evaluate an unchanged x)
+        self._f_eval = 0.0
+        self._g_eval = None
 
     def advance(self) -> bool:
         """Run the optimiser until it needs f and g at ``self.x`` (True) or has finished (False)."""
@@ -78,6 +81,11 @@ class _Chain:
                            self.wa, self.iwa, self.task, self.lsave, self.isave, self.dsave, self.maxls, self.ln_task)
             t = self.task[0]
             if t == 3:
+                if self._x_eval is not None and np.array_equal(self.x, self._x_eval):
+                    # same point requested again: hand back the cached value and gradient, no new evaluation
+                    self.f[()] = self._f_eval
+                    self.g[:] = self._g_eval
+                    continue
                 return True
             if t == 1:
                 self.nit += 1
@@ -92,6 +100,9 @@ class _Chain:
         """f at ``self.x``; the gradient was written into ``self.g`` by the engine."""
         self.f[()] = value
         self.nfev += 1
+        self._x_eval = self.x.copy()
+        self._f_eval = value
+        self._g_eval = self.g.copy()
 
     def result(self) -> OptimizeResult:
         if self.task[0] == 4:
@@ -128,6 +139,11 @@ def run_lockstep(likobj, theta0_list: List[np.ndarray], work, options: Dict, lo:
     n_slots = max(1, min(max_slots or slots_for(n_train), work.count))
     results: Dict[int, object] = {}
     slots = []  # [engine, chain, restart index]
+    import os
+    import time
+    profile = os.environ.get("GPPLUS_LOCKSTEP_PROFILE", "0") != "0"
+    t_begin = time.time()
+    t_setup = 0.0
 
     def start(slot) -> bool:
         """Claim restarts until one needs an evaluation; enqueue it.  False when the queue is drained."""
@@ -146,8 +162,10 @@ def run_lockstep(likobj, theta0_list: List[np.ndarray], work, options: Dict, lo:
     try:
         for _ in range(n_slots):
             i_first = None
+            t0 = time.time()
             eng = model._new_engine(device)
             eng.set_theta_layout(spec)
+            t_setup += time.time() - t0
             slot = [eng, None, i_first]
             slots.append(slot)
             if not start(slot):
@@ -170,6 +188,11 @@ def run_lockstep(likobj, theta0_list: List[np.ndarray], work, options: Dict, lo:
                     start(slot)
             active = [s for s in active if s[1] is not None]
     finally:
+        t_loop = time.time()
         for slot in slots:
             slot[0].close()
+        if profile:
+            print("[lockstep] device %d: %d slots, %d restarts, engine setup %.3f s, total before close %.3f s, "
+                  "close %.3f s" % (device, len(slots), len(results), t_setup, t_loop - t_begin,
+                                    time.time() - t_loop), flush=True)
     return results

@@ -299,15 +299,21 @@ def _run_restarts_lockstep(likobj, theta0_list, work, options, bounds) -> Dict[i
     if bounds is True and len(theta0_list) > 0:
         lo, hi = get_bounds(likobj, theta0_list[0])
     devices = parallel.local_devices()
+    # a driver fills its slots greedily from the shared queue: cap them at this GPU's fair share so that the first
+    # rank / device to start does not claim every restart
+    _, world = parallel.world()
+    share = -(-work.count // max(1, world * len(devices)))
+    n_train = int(likobj.model.train_targets.shape[0])
+    cap = max(1, min(_lockstep.slots_for(n_train), share))
     if len(devices) == 1 or work.count <= 1:
-        return _lockstep.run_lockstep(likobj, theta0_list, work, options, lo, hi, devices[0])
+        return _lockstep.run_lockstep(likobj, theta0_list, work, options, lo, hi, devices[0], cap)
     results: Dict[int, object] = {}
     errors: List[BaseException] = []
     lock = threading.Lock()
 
     def drive(dev):
         try:
-            out = _lockstep.run_lockstep(likobj, theta0_list, work, options, lo, hi, dev)
+            out = _lockstep.run_lockstep(likobj, theta0_list, work, options, lo, hi, dev, cap)
             with lock:
                 results.update(out)
         except BaseException as e:
