@@ -64,9 +64,10 @@ struct PrepArgs {
     const double* centre;  // [dq]
     const double* ztab;    // [n_combo*dz]
     int n, np, dq, dqp, dz, n_combo;
+    int n_pass;            // latent tables (multi-pass ensemble, gp_plus.py:387-399); ztab / zpt hold n_pass blocks
     double* xs;            // [np*dqp]
     double* nrm;           // [np]
-    double* zpt;           // [np*ZP]
+    double* zpt;           // [n_pass][np*ZP]
 };
 
 __global__ void prep_points_kernel(const PrepArgs a) {
@@ -86,11 +87,13 @@ __global__ void prep_points_kernel(const PrepArgs a) {
     }
     a.nrm[i] = nr;
     int lv = (i < a.n && a.level_idx && a.dz > 0) ? a.level_idx[i] : -1;
-    for (int k = 0; k < ZP; k++) {
-        double z = 0.0;
-        if (lv >= 0 && lv < a.n_combo && k < a.dz) z = a.ztab[lv * a.dz + k];
-        a.zpt[(long long)i * ZP + k] = z;
-    }
+    const int passes = a.n_pass > 0 ? a.n_pass : 1;
+    for (int p = 0; p < passes; p++)
+        for (int k = 0; k < ZP; k++) {
+            double z = 0.0;
+            if (lv >= 0 && lv < a.n_combo && k < a.dz) z = a.ztab[((long long)p * a.n_combo + lv) * a.dz + k];
+            a.zpt[((long long)p * a.np + i) * ZP + k] = z;
+        }
 }
 
 // r = y - m(x), diag_add = noise[group] + jitter   (means: gp_plus.py:509-544, noise: multifidelity.py:105-136)
@@ -131,6 +134,10 @@ struct CovArgs {
     const double* alpha;     // optional [cols]: mean_part[tj*ld_part + row] = sum_col K[row,col]*alpha[col]
     double* mean_part;
     long long ld_part;
+    // multi-pass ensemble covariance (gp_plus.py:387-399, 474-482): K = (1/k) sum_p K_p; one launch per latent table
+    int accum;               // add to what `out` / `mean_part` already hold
+    int last;                // last pass: the diagonal additions / identity padding are applied now
+    double scale;            // 1/k (1.0 for the single-pass path: multiplying by it is skipped)
 };
 
 inline size_t cov_smem_bytes(int dqp) {
@@ -255,16 +262,33 @@ __global__ void __launch_bounds__(COV_THREADS, 1) cov_tile_kernel(const CovArgs 
                     kval = sf2 * f;
                     if (HAS_Z) kval *= exp_nonpos(-0.5 * sz);
                 }
-                if (on_diag && a.diag_add) kval += a.diag_add[gi < a.n_r ? gi : 0];
-                if (gi >= a.n_r || gj >= a.n_c) kval = (a.pad_identity && on_diag) ? 1.0 : 0.0;
-                kv[e] = kval;
+                if (a.scale != 1.0) kval *= a.scale;
+                if (gi >= a.n_r || gj >= a.n_c) kval = 0.0;
                 if (a.alpha) msum = fma(kval, sal[col], msum);
+                kv[e] = kval;
             }
             if (a.out) {
+                double2* dst = reinterpret_cast<double2*>(outp + (long long)row * a.ld + wn0 + ni * 8 + 2 * t);
                 double2 v;
                 v.x = kv[0];
                 v.y = kv[1];
-                *reinterpret_cast<double2*>(outp + (long long)row * a.ld + wn0 + ni * 8 + 2 * t) = v;
+                if (a.accum) {
+                    const double2 o = *dst;
+                    v.x += o.x;
+                    v.y += o.y;
+                }
+                if (a.last) {
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const int col = wn0 + ni * 8 + 2 * t + e;
+                        const int gj = tj * CT + col;
+                        const bool on_diag = diag_tile && (row == col);
+                        double& x = e == 0 ? v.x : v.y;
+                        if (on_diag && a.diag_add) x += a.diag_add[gi < a.n_r ? gi : 0];
+                        if (gi >= a.n_r || gj >= a.n_c) x = (a.pad_identity && on_diag) ? 1.0 : 0.0;
+                    }
+                }
+                *dst = v;
             }
         }
         if (a.alpha) {
@@ -275,9 +299,11 @@ __global__ void __launch_bounds__(COV_THREADS, 1) cov_tile_kernel(const CovArgs 
     }
     if (a.alpha) {
         __syncthreads();
-        if (tid < CT)
-            a.mean_part[(long long)tj * a.ld_part + (long long)ti * CT + tid] =
-                (red[tid] + red[CT + tid]) + (red[2 * CT + tid] + red[3 * CT + tid]);
+        if (tid < CT) {
+            double* mp = a.mean_part + (long long)tj * a.ld_part + (long long)ti * CT + tid;
+            const double v = (red[tid] + red[CT + tid]) + (red[2 * CT + tid] + red[3 * CT + tid]);
+            *mp = a.accum ? (*mp + v) : v;
+        }
     }
 }
 
@@ -493,13 +519,13 @@ __global__ void __launch_bounds__(COV_THREADS, 1) grad_tile_kernel(const GradArg
 }
 
 // gz[p][k] = sum_t zpart[t][p][k]
-__global__ void zpart_reduce_kernel(const double* zpart, int T, int np, int n, int dz, double* gz) {
+__global__ void zpart_reduce_kernel(const double* zpart, int T, int np, int n, int dz, double* gz, double scale) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n * dz) return;
     int p = idx / dz, k = idx - p * dz;
     double s = 0.0;
     for (int t = 0; t < T; t++) s += zpart[((long long)t * np + p) * ZP + k];
-    gz[idx] = s;
+    gz[idx] = (scale != 1.0) ? s * scale : s;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -528,6 +554,7 @@ struct FinishArgs {
     const int* mean_idx;
     const int* info;
     int n, np, T, dq, dqp, n_noise, n_mean, want_grad;
+    int n_pass;                 // tile_part holds n_pass blocks (one gradient pass per latent table); averaged here
     double* res;  // [0]=quad [1]=logdet [2]=info [3]=d_sf2 [4..4+dq)=d_w, then d_noise[n_noise], d_beta[n_mean]
 };
 
@@ -548,16 +575,19 @@ __global__ void __launch_bounds__(256) finish_kernel(const FinishArgs a) {
     if (!a.want_grad) return;
     const int ntiles = a.T * (a.T + 1) / 2;
     const int tp = 1 + a.dqp;
+    const int passes = a.n_pass > 0 ? a.n_pass : 1;
     for (int c = 0; c < 1 + a.dq; c++) {
         double s = 0.0;
         // tile id b = ti(ti+1)/2 + tj ; diagonal tiles (tj == ti) weigh 1, the others 2
-        for (int b = tid; b < ntiles; b += 256) {
-            int ti, tj;
-            tri_decode(b, ti, tj);
-            double wgt = (ti == tj) ? 1.0 : 2.0;
-            s = fma(wgt, a.tile_part[(long long)b * tp + c], s);
-        }
+        for (int p = 0; p < passes; p++)
+            for (int b = tid; b < ntiles; b += 256) {
+                int ti, tj;
+                tri_decode(b, ti, tj);
+                double wgt = (ti == tj) ? 1.0 : 2.0;
+                s = fma(wgt, a.tile_part[((long long)p * ntiles + b) * tp + c], s);
+            }
         s = block_sum_256(s, sh);
+        if (passes > 1) s /= (double)passes;
         if (tid == 0) {
             if (c == 0) a.res[3] = -0.5 * s;
             else a.res[3 + c] = -0.5 * s / a.w[c - 1];

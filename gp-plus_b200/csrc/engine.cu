@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -52,10 +53,11 @@ struct gpp_handle {
     long long n = 0, np = 0;
     int T = 0;
     int dq = 0, dqp = 0, dz = 0, n_combo = 0, n_noise = 0, n_mean = 0, kernel = 0;
+    int n_pass = 1;  // latent tables averaged into K (multi-pass ensemble covariance, gp_plus.py:387-399)
     // static training data
     double *xq = nullptr, *y = nullptr, *centre = nullptr;
     int *level_idx = nullptr, *noise_idx = nullptr, *mean_idx = nullptr;
-    // hyper-parameters (device copy): [w dq | ztab n_combo*dz | noise | beta]
+    // hyper-parameters (device copy): [w dq | ztab n_pass*n_combo*dz | noise | beta]
     double* hyp = nullptr;
     double* hyp_host = nullptr;  // pinned
     int hyp_len = 0;
@@ -100,6 +102,8 @@ struct gpp_handle {
     bool pending = false;    // gpp_objective_enqueue issued, gpp_objective_collect not yet called
     int pending_grad = 0;
     void* slab = nullptr;         // one device allocation holds every per-handle buffer below (gpp_create)
+    size_t slab_bytes = 0;
+    int* idx_slots[3] = {nullptr, nullptr, nullptr};  // storage of level_idx / noise_idx / mean_idx inside the slab
     void* pinned_slab = nullptr;  // one pinned allocation holds hyp_host / info_host / res_host / gz_host
     gpp_stats stats;
     cudaEvent_t ev_info = nullptr;                 // factorisation status available (jitter-ladder early-out)
@@ -109,13 +113,14 @@ struct gpp_handle {
 
 static const double* hyp_w(const gpp_handle* h) { return h->hyp; }
 static const double* hyp_z(const gpp_handle* h) { return h->hyp + h->dq; }
-static const double* hyp_noise(const gpp_handle* h) { return h->hyp + h->dq + h->n_combo * h->dz; }
-static const double* hyp_beta(const gpp_handle* h) { return h->hyp + h->dq + h->n_combo * h->dz + h->n_noise; }
+static int ztab_len(const gpp_handle* h) { return h->n_pass * h->n_combo * h->dz; }
+static const double* hyp_noise(const gpp_handle* h) { return h->hyp + h->dq + ztab_len(h); }
+static const double* hyp_beta(const gpp_handle* h) { return h->hyp + h->dq + ztab_len(h) + h->n_noise; }
 // per-evaluation scalars live behind the vectors so that graph replays need no new kernel arguments
 static const double* hyp_sf2(const gpp_handle* h) { return hyp_beta(h) + h->n_mean; }
 static const double* hyp_jitter(const gpp_handle* h) { return hyp_beta(h) + h->n_mean + 1; }
 
-extern "C" int gpp_version(void) { return 103; }
+extern "C" int gpp_version(void) { return 105; }
 
 extern "C" int gpp_device_count(void) {
     int c = 0;
@@ -135,7 +140,7 @@ static cudaError_t dev_alloc(Tp** p, size_t count) {
     return cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(Tp));
 }
 
-extern "C" void gpp_destroy(gpp_handle* h) {
+static void destroy_now(gpp_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->st) cudaStreamSynchronize(h->st);
@@ -154,6 +159,105 @@ extern "C" void gpp_destroy(gpp_handle* h) {
     delete h;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Handle pool.  Creating a handle costs one cudaMalloc + one cudaMallocHost + three streams + a dozen events + two
+// CUDA-graph instantiations, destroying it a synchronising cudaFree / cudaFreeHost: 5-25 ms each way on the GPU box,
+// i.e. seconds for the 64 handles of a lock-step multi-start fit of a small model -- more than the fit itself.
+// Released handles of small problems are therefore parked and handed back to the next gpp_create with the SAME
+// shape on the same device (only the training data are re-uploaded; captured graphs stay valid because every
+// device address and size is unchanged).  gpp_pool_clear() frees them.
+static std::mutex g_pool_mu;
+static std::vector<gpp_handle*> g_pool;
+static size_t g_pool_bytes = 0;
+static const size_t kPoolMaxHandleBytes = 192ull << 20;  // handles up to Np = 2816 (3 x Np^2 doubles)
+static const size_t kPoolMaxBytes = 6ull << 30;
+static const size_t kPoolMaxHandles = 160;
+
+static bool same_shape(const gpp_handle* h, const gpp_problem* p, int device) {
+    return h->device == device && h->n == p->n && h->dq == p->dq && h->dz == p->dz &&
+           h->n_combo == (p->dz > 0 ? p->n_combo : 0) && h->n_noise == p->n_noise && h->n_mean == p->n_mean &&
+           h->kernel == p->kernel && h->n_pass == (p->n_pass > 1 ? p->n_pass : 1) && (h->level_idx != nullptr) == (p->dz > 0 && p->level_idx != nullptr) &&
+           (h->noise_idx != nullptr) == (p->noise_idx != nullptr) && (h->mean_idx != nullptr) == (p->mean_idx != nullptr);
+}
+
+extern "C" void gpp_pool_clear(void) {
+    std::vector<gpp_handle*> victims;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        victims.swap(g_pool);
+        g_pool_bytes = 0;
+    }
+    for (gpp_handle* h : victims) destroy_now(h);
+}
+
+extern "C" void gpp_destroy(gpp_handle* h) {
+    if (!h) return;
+    const char* e = getenv("GPP_POOL");
+    const bool pooling = !(e && atoi(e) == 0);
+    if (pooling && h->slab_bytes <= kPoolMaxHandleBytes && h->mc_alloc == 0) {
+        cudaSetDevice(h->device);
+        if (h->st) cudaStreamSynchronize(h->st);
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        if (g_pool.size() < kPoolMaxHandles && g_pool_bytes + h->slab_bytes <= kPoolMaxBytes) {
+            h->layout.set = false;
+            h->factorized = false;
+            h->pending = false;
+            g_pool.push_back(h);
+            g_pool_bytes += h->slab_bytes;
+            return;
+        }
+    }
+    destroy_now(h);
+}
+
+// training data of `p` into the (new or recycled) handle
+static int upload_problem(gpp_handle* h, const gpp_problem* p) {
+    const long long n = h->n;
+    if (h->dq > 0) CK(cudaMemcpy(h->xq, p->xq, sizeof(double) * n * h->dq, cudaMemcpyDefault));
+    CK(cudaMemcpy(h->y, p->y, sizeof(double) * n, cudaMemcpyDefault));
+    {
+        // column means of the training inputs (the centring of gpytorch's covar_dist)
+        std::vector<double> xh((size_t)n * std::max(h->dq, 1)), c(std::max(h->dq, 1), 0.0);
+        if (h->dq > 0) CK(cudaMemcpy(xh.data(), p->xq, sizeof(double) * n * h->dq, cudaMemcpyDefault));
+        for (int d = 0; d < h->dq; d++) {
+            double sacc = 0.0;
+            for (long long i = 0; i < n; i++) sacc += xh[i * h->dq + d];
+            c[d] = sacc / (double)n;
+        }
+        CK(cudaMemcpy(h->centre, c.data(), sizeof(double) * std::max(h->dq, 1), cudaMemcpyHostToDevice));
+    }
+    auto upload_idx = [&](const int32_t* src, int* slot, int** dst, int hi, const char* name) -> int {
+        *dst = nullptr;
+        if (!src) return GPP_OK;
+        std::vector<int> tmp((size_t)n);
+        cudaError_t e = cudaMemcpy(tmp.data(), src, sizeof(int) * n, cudaMemcpyDefault);
+        if (e != cudaSuccess) {
+            set_err("index upload", e);
+            return GPP_ERR_CUDA;
+        }
+        for (long long i = 0; i < n; i++)
+            if (tmp[i] >= hi || tmp[i] < -1) {
+                g_err = std::string("gpp_create: ") + name + " out of range";
+                return GPP_ERR_ARG;
+            }
+        e = cudaMemcpy(slot, tmp.data(), sizeof(int) * n, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            set_err("index upload", e);
+            return GPP_ERR_CUDA;
+        }
+        *dst = slot;
+        if (dst == &h->level_idx) h->level_idx_host = tmp;
+        return GPP_OK;
+    };
+    int rc;
+    if (h->dz > 0 && (rc = upload_idx(p->level_idx, h->idx_slots[0], &h->level_idx, h->n_combo, "level_idx")) != GPP_OK)
+        return rc;
+    if ((rc = upload_idx(p->noise_idx, h->idx_slots[1], &h->noise_idx, h->n_noise, "noise_idx")) != GPP_OK) return rc;
+    if ((rc = upload_idx(p->mean_idx, h->idx_slots[2], &h->mean_idx, std::max(h->n_mean, 1), "mean_idx")) != GPP_OK)
+        return rc;
+    return GPP_OK;
+}
+
 extern "C" int gpp_create(const gpp_problem* p, int device, gpp_handle** out) {
     if (!p || !out) ARG_FAIL("gpp_create: null argument");
     *out = nullptr;
@@ -164,6 +268,8 @@ extern "C" int gpp_create(const gpp_problem* p, int device, gpp_handle** out) {
     if (p->dz > 0 && (p->n_combo <= 0 || !p->level_idx)) ARG_FAIL("gpp_create: latent map needs n_combo and level_idx");
     if (p->n_noise < 1 || p->n_mean < 0) ARG_FAIL("gpp_create: n_noise must be >= 1 and n_mean >= 0");
     if (p->kernel < 0 || p->kernel > 2) ARG_FAIL("gpp_create: unknown kernel");
+    if (p->n_pass < 0 || p->n_pass > 64) ARG_FAIL("gpp_create: n_pass out of range (0..64)");
+    if (p->n_pass > 1 && p->dz == 0) ARG_FAIL("gpp_create: several latent passes need a latent map (dz > 0)");
     if ((p->dq > 0 && !p->xq) || !p->y) ARG_FAIL("gpp_create: xq / y missing");
     int ndev = gpp_device_count();
     if (ndev <= 0) {
@@ -177,6 +283,31 @@ extern "C" int gpp_create(const gpp_problem* p, int device, gpp_handle** out) {
     if (prop.major < 10) {
         g_err = "gpp_create: built for sm_100a (B200); device compute capability is too old";
         return GPP_ERR_CUDA;
+    }
+
+    {
+        // a parked handle of the same shape on this device: re-upload the data, keep everything else
+        gpp_handle* reuse = nullptr;
+        {
+            std::lock_guard<std::mutex> lk(g_pool_mu);
+            for (size_t i = 0; i < g_pool.size(); i++)
+                if (same_shape(g_pool[i], p, device)) {
+                    reuse = g_pool[i];
+                    g_pool_bytes -= reuse->slab_bytes;
+                    g_pool.erase(g_pool.begin() + (long)i);
+                    break;
+                }
+        }
+        if (reuse) {
+            memset(&reuse->stats, 0, sizeof(reuse->stats));
+            int rc = upload_problem(reuse, p);
+            if (rc != GPP_OK) {
+                destroy_now(reuse);
+                return rc;
+            }
+            *out = reuse;
+            return GPP_OK;
+        }
     }
 
     gpp_handle* h = new gpp_handle();
@@ -194,6 +325,7 @@ extern "C" int gpp_create(const gpp_problem* p, int device, gpp_handle** out) {
     h->n_noise = p->n_noise;
     h->n_mean = p->n_mean;
     h->kernel = p->kernel;
+    h->n_pass = p->n_pass > 1 ? p->n_pass : 1;
     const long long n = h->n, np = h->np;
     const int T = h->T;
 
@@ -202,7 +334,7 @@ extern "C" int gpp_create(const gpp_problem* p, int device, gpp_handle** out) {
         cudaError_t e_ = (x);     \
         if (e_ != cudaSuccess) {  \
             set_err(#x, e_);      \
-            gpp_destroy(h);       \
+            destroy_now(h);       \
             return GPP_ERR_CUDA;  \
         }                         \
     } while (0)
@@ -238,7 +370,7 @@ extern "C" int gpp_create(const gpp_problem* p, int device, gpp_handle** out) {
     }
     CKH(h->la.init(h->T));
 
-    h->hyp_len = h->dq + h->n_combo * h->dz + h->n_noise + h->n_mean + 2;
+    h->hyp_len = h->dq + h->n_pass * h->n_combo * h->dz + h->n_noise + h->n_mean + 2;
     h->res_len = 4 + h->dq + h->n_noise + h->n_mean;
     {
         // ONE device allocation and ONE pinned allocation per handle: the lock-step multi-start driver creates up to
@@ -253,12 +385,13 @@ extern "C" int gpp_create(const gpp_problem* p, int device, gpp_handle** out) {
         const size_t o_xq = take(D * n * h->dq), o_y = take(D * n), o_centre = take(D * std::max(h->dq, 1));
         const size_t o_lvl = take(I * n), o_nidx = take(I * n), o_midx = take(I * n);
         const size_t o_hyp = take(D * h->hyp_len), o_xs = take(D * np * h->dqp), o_nrm = take(D * np);
-        const size_t o_zpt = take(D * np * ZP), o_r = take(D * np), o_da = take(D * np), o_v = take(D * np);
+        const size_t o_zpt = take(D * h->n_pass * np * ZP), o_r = take(D * np), o_da = take(D * np), o_v = take(D * np);
         const size_t o_alpha = take(D * np), o_part = take(D * T * np);
         const size_t o_A = take(D * np * np), o_M = take(D * np * np), o_S = take(D * np * np);
         const size_t o_ld = take(D * T), o_info = take(I);
-        const size_t o_tp = take(D * (size_t)T * (T + 1) / 2 * (1 + h->dqp));
-        const size_t o_zpart = take(h->dz > 0 ? D * T * np * ZP : 8), o_gz = take(h->dz > 0 ? D * n * h->dz : 8);
+        const size_t o_tp = take(D * h->n_pass * (size_t)T * (T + 1) / 2 * (1 + h->dqp));
+        const size_t o_zpart = take(h->dz > 0 ? D * h->n_pass * T * np * ZP : 8);
+        const size_t o_gz = take(h->dz > 0 ? D * h->n_pass * n * h->dz : 8);
         const size_t o_res = take(D * h->res_len);
         CKH(cudaMalloc(&h->slab, off));
         char* base = (char*)h->slab;
@@ -285,7 +418,10 @@ extern "C" int gpp_create(const gpp_problem* p, int device, gpp_handle** out) {
             h->gz = (double*)(base + o_gz);
         }
         h->res = (double*)(base + o_res);
-        int* idx_slots[3] = {(int*)(base + o_lvl), (int*)(base + o_nidx), (int*)(base + o_midx)};
+        h->idx_slots[0] = (int*)(base + o_lvl);
+        h->idx_slots[1] = (int*)(base + o_nidx);
+        h->idx_slots[2] = (int*)(base + o_midx);
+        h->slab_bytes = off;
 
         size_t poff = 0;
         auto ptake = [&](size_t bytes) {
@@ -294,60 +430,18 @@ extern "C" int gpp_create(const gpp_problem* p, int device, gpp_handle** out) {
             return at;
         };
         const size_t p_hyp = ptake(D * h->hyp_len), p_info = ptake(I), p_res = ptake(D * h->res_len);
-        const size_t p_gz = ptake(h->dz > 0 ? D * n * h->dz : 8);
+        const size_t p_gz = ptake(h->dz > 0 ? D * h->n_pass * n * h->dz : 8);
         CKH(cudaMallocHost(&h->pinned_slab, poff));
         char* pb = (char*)h->pinned_slab;
         h->hyp_host = (double*)(pb + p_hyp);
         h->info_host = (int*)(pb + p_info);
         h->res_host = (double*)(pb + p_res);
         if (h->dz > 0) h->gz_host = (double*)(pb + p_gz);
-
-        if (h->dq > 0) CKH(cudaMemcpy(h->xq, p->xq, sizeof(double) * n * h->dq, cudaMemcpyDefault));
-        CKH(cudaMemcpy(h->y, p->y, sizeof(double) * n, cudaMemcpyDefault));
-        {
-            // column means of the training inputs (the centring of gpytorch's covar_dist)
-            std::vector<double> xh((size_t)n * std::max(h->dq, 1)), c(std::max(h->dq, 1), 0.0);
-            if (h->dq > 0) CKH(cudaMemcpy(xh.data(), p->xq, sizeof(double) * n * h->dq, cudaMemcpyDefault));
-            for (int d = 0; d < h->dq; d++) {
-                double sacc = 0.0;
-                for (long long i = 0; i < n; i++) sacc += xh[i * h->dq + d];
-                c[d] = sacc / (double)n;
-            }
-            CKH(cudaMemcpy(h->centre, c.data(), sizeof(double) * std::max(h->dq, 1), cudaMemcpyHostToDevice));
-        }
-        auto upload_idx = [&](const int32_t* src, int* slot, int** dst, int hi, const char* name) -> int {
-            if (!src) return GPP_OK;
-            std::vector<int> tmp((size_t)n);
-            cudaError_t e = cudaMemcpy(tmp.data(), src, sizeof(int) * n, cudaMemcpyDefault);
-            if (e != cudaSuccess) {
-                set_err("index upload", e);
-                return GPP_ERR_CUDA;
-            }
-            for (long long i = 0; i < n; i++)
-                if (tmp[i] >= hi || tmp[i] < -1) {
-                    g_err = std::string("gpp_create: ") + name + " out of range";
-                    return GPP_ERR_ARG;
-                }
-            e = cudaMemcpy(slot, tmp.data(), sizeof(int) * n, cudaMemcpyHostToDevice);
-            if (e != cudaSuccess) {
-                set_err("index upload", e);
-                return GPP_ERR_CUDA;
-            }
-            *dst = slot;
-            if (dst == &h->level_idx) h->level_idx_host = tmp;
-            return GPP_OK;
-        };
-        int rc;
-        if (h->dz > 0 && (rc = upload_idx(p->level_idx, idx_slots[0], &h->level_idx, h->n_combo, "level_idx")) != GPP_OK) {
-            gpp_destroy(h);
-            return rc;
-        }
-        if ((rc = upload_idx(p->noise_idx, idx_slots[1], &h->noise_idx, h->n_noise, "noise_idx")) != GPP_OK) {
-            gpp_destroy(h);
-            return rc;
-        }
-        if ((rc = upload_idx(p->mean_idx, idx_slots[2], &h->mean_idx, std::max(h->n_mean, 1), "mean_idx")) != GPP_OK) {
-            gpp_destroy(h);
+    }
+    {
+        int rc = upload_problem(h, p);
+        if (rc != GPP_OK) {
+            destroy_now(h);
             return rc;
         }
     }
@@ -388,7 +482,7 @@ static void fill_hyper_host(gpp_handle* h, const gpp_hyper* hy, double jitter) {
     double* hh = h->hyp_host;
     int o = 0;
     for (int d = 0; d < h->dq; d++) hh[o++] = hy->w[d];
-    for (int k = 0; k < h->n_combo * h->dz; k++) hh[o++] = hy->z[k];
+    for (int k = 0; k < ztab_len(h); k++) hh[o++] = hy->z[k];
     for (int k = 0; k < h->n_noise; k++) hh[o++] = hy->noise[k];
     for (int k = 0; k < h->n_mean; k++) hh[o++] = hy->beta[k];
     hh[o++] = hy->sigma_f2;
@@ -411,6 +505,7 @@ static int stage_prep(gpp_handle* h) {
     pa.dqp = h->dqp;
     pa.dz = h->dz;
     pa.n_combo = h->n_combo;
+    pa.n_pass = h->n_pass;
     pa.xs = h->xs;
     pa.nrm = h->nrm;
     pa.zpt = h->zpt;
@@ -433,7 +528,6 @@ static int stage_factor(gpp_handle* h) {
     memset(&ca, 0, sizeof(ca));
     ca.xs_r = ca.xs_c = h->xs;
     ca.nrm_r = ca.nrm_c = h->nrm;
-    ca.zpt_r = ca.zpt_c = h->zpt;
     ca.out = h->A;
     ca.ld = h->np;
     ca.n_r = ca.n_c = (int)h->n;
@@ -446,7 +540,13 @@ static int stage_factor(gpp_handle* h) {
     ca.sf2 = h->sf2;
     ca.sf2_dev = hyp_sf2(h);
     ca.diag_add = h->diag_add;
-    CK(launch_cov(ca, h->kernel, h->st));
+    ca.scale = 1.0 / (double)h->n_pass;
+    for (int p = 0; p < h->n_pass; p++) {  // K = (1/k) sum_p K_p: one launch per latent table
+        ca.zpt_r = ca.zpt_c = h->zpt + (size_t)p * h->np * ZP;
+        ca.accum = p > 0;
+        ca.last = p == h->n_pass - 1;
+        CK(launch_cov(ca, h->kernel, h->st));
+    }
     mark(h, EV_COV);
     if (h->use_lookahead)
         CK(potrf_lookahead(h->A, h->M, (int)h->np, h->T, h->logdet_part, h->info, h->st, h->la, h->S));
@@ -487,7 +587,6 @@ static int stage_grad(gpp_handle* h) {
     memset(&ga, 0, sizeof(ga));
     ga.xs = h->xs;
     ga.nrm = h->nrm;
-    ga.zpt = h->zpt;
     ga.alpha = h->alpha;
     ga.Kinv = h->S;
     ga.ld = h->np;
@@ -499,16 +598,26 @@ static int stage_grad(gpp_handle* h) {
     ga.dz = h->dz;
     ga.sf2 = h->sf2;
     ga.sf2_dev = hyp_sf2(h);
-    ga.tile_part = h->tile_part;
-    ga.zpart = h->zpart;
-    CK(launch_grad(ga, h->kernel, h->st));
-    if (h->dz > 0) {
-        const int cnt = (int)(h->n * h->dz);
-        zpart_reduce_kernel<<<(cnt + 255) / 256, 256, 0, h->st>>>(h->zpart, h->T, (int)h->np, (int)h->n, h->dz, h->gz);
-        CK(cudaGetLastError());
-    count_launch();
-        CK(cudaMemcpyAsync(h->gz_host, h->gz, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->st));
+    const size_t tp_stride = (size_t)h->T * (h->T + 1) / 2 * (1 + h->dqp);
+    const size_t zp_stride = (size_t)h->T * h->np * ZP;
+    // every gradient component is linear in K, so the gradient of the averaged covariance is the average of the
+    // single-table gradients evaluated with the SAME W = alpha alpha^T - K_y^-1: one pass per latent table
+    for (int p = 0; p < h->n_pass; p++) {
+        ga.zpt = h->zpt + (size_t)p * h->np * ZP;
+        ga.tile_part = h->tile_part + p * tp_stride;
+        ga.zpart = h->dz > 0 ? h->zpart + p * zp_stride : nullptr;
+        CK(launch_grad(ga, h->kernel, h->st));
+        if (h->dz > 0) {
+            const int cnt = (int)(h->n * h->dz);
+            zpart_reduce_kernel<<<(cnt + 255) / 256, 256, 0, h->st>>>(ga.zpart, h->T, (int)h->np, (int)h->n, h->dz,
+                                                                      h->gz + (size_t)p * cnt, 1.0 / (double)h->n_pass);
+            CK(cudaGetLastError());
+            count_launch();
+        }
     }
+    if (h->dz > 0)
+        CK(cudaMemcpyAsync(h->gz_host, h->gz, sizeof(double) * h->n_pass * h->n * h->dz, cudaMemcpyDeviceToHost,
+                           h->st));
     mark(h, EV_GRAD);
     return GPP_OK;
 }
@@ -534,6 +643,7 @@ static int stage_finish(gpp_handle* h, int want_grad) {
     fa.n_noise = h->n_noise;
     fa.n_mean = h->n_mean;
     fa.want_grad = want_grad;
+    fa.n_pass = h->n_pass;
     fa.res = h->res;
     finish_kernel<<<1, 256, 0, h->st>>>(fa);
     CK(cudaGetLastError());
@@ -678,11 +788,15 @@ static int collect_mll(gpp_handle* h, int want_grad, gpp_mll_result* out) {
             for (int k = 0; k < h->n_mean; k++) out->d_beta[k] = r[4 + h->dq + h->n_noise + k];
         if (out->d_z && h->dz > 0) {
             // d nll / d Z[a] = sum_{i in a} sum_j P_ij (z_i - z_j): scatter the per-point sums by level
-            for (int k = 0; k < h->n_combo * h->dz; k++) out->d_z[k] = 0.0;
-            for (long long i = 0; i < h->n; i++) {
-                int a = h->level_idx_host[(size_t)i];
-                if (a < 0) continue;
-                for (int k = 0; k < h->dz; k++) out->d_z[a * h->dz + k] += h->gz_host[i * h->dz + k];
+            for (int k = 0; k < ztab_len(h); k++) out->d_z[k] = 0.0;
+            for (int p = 0; p < h->n_pass; p++) {
+                double* dz_p = out->d_z + (size_t)p * h->n_combo * h->dz;
+                const double* gz_p = h->gz_host + (size_t)p * h->n * h->dz;
+                for (long long i = 0; i < h->n; i++) {
+                    int a = h->level_idx_host[(size_t)i];
+                    if (a < 0) continue;
+                    for (int k = 0; k < h->dz; k++) dz_p[a * h->dz + k] += gz_p[i * h->dz + k];
+                }
             }
         }
     } else {
@@ -713,13 +827,14 @@ extern "C" int gpp_mll_grad(gpp_handle* h, const gpp_hyper* hy, int want_grad, g
 
 extern "C" int gpp_set_theta_layout(gpp_handle* h, const gpp_theta_layout* layout) {
     if (!h || !layout) ARG_FAIL("gpp_set_theta_layout: null argument");
+    if (h->n_pass > 1) ARG_FAIL("gpp_set_theta_layout: the closed-form layout covers the single-pass latent map only");
     const char* err = layout_copy(h->layout, layout, h->dq, h->dz, h->n_combo, h->n_noise, h->n_mean);
     if (err) {
         h->layout.set = false;
         ARG_FAIL(err);
     }
     h->g_w.assign(std::max(h->dq, 1), 0.0);
-    h->g_z.assign(std::max(h->n_combo * h->dz, 1), 0.0);
+    h->g_z.assign(std::max(h->n_pass * h->n_combo * h->dz, 1), 0.0);
     h->g_noise.assign(std::max(h->n_noise, 1), 0.0);
     h->g_beta.assign(std::max(h->n_mean, 1), 0.0);
     return GPP_OK;
@@ -858,7 +973,6 @@ extern "C" int gpp_covariance(gpp_handle* h, const gpp_hyper* hy, double* k_out)
     memset(&ca, 0, sizeof(ca));
     ca.xs_r = ca.xs_c = h->xs;
     ca.nrm_r = ca.nrm_c = h->nrm;
-    ca.zpt_r = ca.zpt_c = h->zpt;
     ca.out = h->S;
     ca.ld = h->np;
     ca.n_r = ca.n_c = (int)h->n;
@@ -869,7 +983,13 @@ extern "C" int gpp_covariance(gpp_handle* h, const gpp_hyper* hy, double* k_out)
     ca.dqp = h->dqp;
     ca.dz = h->dz;
     ca.sf2 = h->sf2;
-    CK(launch_cov(ca, h->kernel, h->st));
+    ca.scale = 1.0 / (double)h->n_pass;
+    for (int p = 0; p < h->n_pass; p++) {
+        ca.zpt_r = ca.zpt_c = h->zpt + (size_t)p * h->np * ZP;
+        ca.accum = p > 0;
+        ca.last = p == h->n_pass - 1;
+        CK(launch_cov(ca, h->kernel, h->st));
+    }
     CK(cudaMemcpy2DAsync(k_out, sizeof(double) * h->n, h->S, sizeof(double) * h->np, sizeof(double) * h->n, h->n,
                          cudaMemcpyDefault, h->st));
     CK(cudaStreamSynchronize(h->st));
@@ -939,7 +1059,7 @@ static int ensure_chunk_buffers(gpp_handle* h, long long m) {
     CK(dev_alloc(&h->c_xq, mc * std::max(h->dq, 1)));
     CK(dev_alloc(&h->c_xs, mc * h->dqp));
     CK(dev_alloc(&h->c_nrm, mc));
-    CK(dev_alloc(&h->c_zpt, mc * ZP));
+    CK(dev_alloc(&h->c_zpt, mc * ZP * h->n_pass));
     CK(dev_alloc(&h->c_K, mc * (size_t)h->np));
     CK(dev_alloc(&h->c_lvl, mc));
     CK(dev_alloc(&h->c_noise, mc));
@@ -1022,6 +1142,7 @@ static int predict_impl(gpp_handle* h, long long m, const double* xq, const int3
         pa.dqp = h->dqp;
         pa.dz = h->dz;
         pa.n_combo = h->n_combo;
+        pa.n_pass = h->n_pass;
         pa.xs = h->c_xs;
         pa.nrm = h->c_nrm;
         pa.zpt = h->c_zpt;
@@ -1033,10 +1154,8 @@ static int predict_impl(gpp_handle* h, long long m, const double* xq, const int3
         memset(&ca, 0, sizeof(ca));
         ca.xs_r = h->c_xs;
         ca.nrm_r = h->c_nrm;
-        ca.zpt_r = h->c_zpt;
         ca.xs_c = h->xs;
         ca.nrm_c = h->nrm;
-        ca.zpt_c = h->zpt;
         ca.out = h->c_K;
         ca.ld = h->np;
         ca.n_r = (int)mc;
@@ -1049,7 +1168,14 @@ static int predict_impl(gpp_handle* h, long long m, const double* xq, const int3
         ca.alpha = h->alpha;
         ca.mean_part = h->c_mean_part;
         ca.ld_part = MC;
-        CK(launch_cov(ca, h->kernel, h->st));
+        ca.scale = 1.0 / (double)h->n_pass;
+        for (int p = 0; p < h->n_pass; p++) {
+            ca.zpt_r = h->c_zpt + (size_t)p * mcp * ZP;
+            ca.zpt_c = h->zpt + (size_t)p * h->np * ZP;
+            ca.accum = p > 0;
+            ca.last = p == h->n_pass - 1;
+            CK(launch_cov(ca, h->kernel, h->st));
+        }
 
         GemmOp op = gemm_default();  // V = K* L^-T, only its row sums of squares are kept
         op.A = h->c_K;

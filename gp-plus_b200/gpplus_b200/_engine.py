@@ -20,7 +20,8 @@ MAX_DQ, MAX_DZ = 32, 4
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libgpplus_b200.so")
 
 EXPORTS = (
-    "gpp_version", "gpp_device_count", "gpp_last_error", "gpp_launch_count", "gpp_create", "gpp_destroy", "gpp_mll_grad",
+    "gpp_version", "gpp_device_count", "gpp_last_error", "gpp_launch_count", "gpp_create", "gpp_destroy", "gpp_pool_clear",
+    "gpp_mll_grad",
     "gpp_get_timings", "gpp_get_stats", "gpp_covariance", "gpp_fetch", "gpp_factorize", "gpp_predict", "gpp_acq_argmax",
     "gpp_probe_dgemm", "gpp_set_theta_layout", "gpp_objective", "gpp_objective_enqueue", "gpp_objective_collect",
 )
@@ -47,7 +48,8 @@ _ip = C.POINTER(C.c_int32)
 class _Problem(C.Structure):
     _fields_ = [("n", C.c_int64), ("dq", C.c_int32), ("dz", C.c_int32), ("n_combo", C.c_int32),
                 ("n_noise", C.c_int32), ("n_mean", C.c_int32), ("kernel", C.c_int32),
-                ("xq", _dp), ("y", _dp), ("level_idx", _ip), ("noise_idx", _ip), ("mean_idx", _ip)]
+                ("xq", _dp), ("y", _dp), ("level_idx", _ip), ("noise_idx", _ip), ("mean_idx", _ip),
+                ("n_pass", C.c_int32)]
 
 
 class _Hyper(C.Structure):
@@ -104,6 +106,8 @@ def load_library():
         lib.gpp_create.restype = C.c_int
         lib.gpp_destroy.argtypes = [C.c_void_p]
         lib.gpp_destroy.restype = None
+        lib.gpp_pool_clear.argtypes = []
+        lib.gpp_pool_clear.restype = None
         lib.gpp_mll_grad.argtypes = [C.c_void_p, C.POINTER(_Hyper), C.c_int, C.POINTER(_MllResult)]
         lib.gpp_mll_grad.restype = C.c_int
         lib.gpp_get_timings.argtypes = [C.c_void_p, C.POINTER(_Timings)]
@@ -140,6 +144,11 @@ def load_library():
 def launch_count() -> int:
     """CUDA kernels launched by the library in this process so far."""
     return int(load_library().gpp_launch_count())
+
+
+def pool_clear():
+    """Free every parked engine handle (see gpp_destroy in include/gpplus_b200.h)."""
+    load_library().gpp_pool_clear()
 
 
 def device_count() -> int:
@@ -184,7 +193,7 @@ class Engine:
     """One training set resident on one GPU (``gpp_handle``).  Not thread-safe; use one per in-flight restart."""
 
     def __init__(self, xq, y, kernel: int, level_idx=None, n_combo: int = 0, dz: int = 0, noise_idx=None,
-                 n_noise: int = 1, mean_idx=None, n_mean: int = 1, device: int = 0):
+                 n_noise: int = 1, mean_idx=None, n_mean: int = 1, device: int = 0, n_pass: int = 1):
         lib = load_library()
         y = _f64(y).reshape(-1)
         n = y.shape[0]
@@ -192,10 +201,12 @@ class Engine:
         self.n, self.dq, self.dz = n, xq.shape[1], int(dz)
         self.n_combo, self.n_noise, self.n_mean, self.kernel = int(n_combo), int(n_noise), int(n_mean), int(kernel)
         self.device = int(device)
+        self.n_pass = max(1, int(n_pass))
         self._keep = (xq, y, _i32(level_idx, n), _i32(noise_idx, n), _i32(mean_idx, n))
         p = _Problem()
         p.n, p.dq, p.dz, p.n_combo = n, self.dq, self.dz, self.n_combo
         p.n_noise, p.n_mean, p.kernel = self.n_noise, self.n_mean, self.kernel
+        p.n_pass = self.n_pass
         p.xq = xq.ctypes.data_as(_dp) if self.dq > 0 else None
         p.y = y.ctypes.data_as(_dp)
         for name, arr in zip(("level_idx", "noise_idx", "mean_idx"), self._keep[2:]):
@@ -226,8 +237,8 @@ class Engine:
         z = None
         if self.dz > 0:
             z = _f64(hyper["z"]).reshape(-1)
-            if z.shape[0] != self.n_combo * self.dz:
-                raise ValueError("hyper['z'] must be [n_combo, dz]")
+            if z.shape[0] != self.n_pass * self.n_combo * self.dz:
+                raise ValueError("hyper['z'] must be [n_combo, dz] (or [n_pass, n_combo, dz])")
         noise = _f64(hyper["noise"]).reshape(-1)
         if noise.shape[0] != self.n_noise:
             raise ValueError("hyper['noise'] must have %d entries" % self.n_noise)
@@ -249,7 +260,7 @@ class Engine:
         hy, keep = self._hyper(hyper)
         res = _MllResult()
         d_w = np.zeros(max(self.dq, 1))
-        d_z = np.zeros(max(self.n_combo * self.dz, 1))
+        d_z = np.zeros(max(self.n_pass * self.n_combo * self.dz, 1))
         d_noise = np.zeros(self.n_noise)
         d_beta = np.zeros(max(self.n_mean, 1))
         res.d_w, res.d_z = d_w.ctypes.data_as(_dp), d_z.ctypes.data_as(_dp)
@@ -264,7 +275,8 @@ class Engine:
             out["d_w"] = d_w[: self.dq].copy()
             out["d_noise"] = d_noise
             if self.dz > 0:
-                out["d_z"] = d_z.reshape(self.n_combo, self.dz)
+                out["d_z"] = d_z.reshape(self.n_combo, self.dz) if self.n_pass == 1 else \
+                    d_z.reshape(self.n_pass, self.n_combo, self.dz)
             if self.n_mean > 0:
                 out["d_beta"] = d_beta[: self.n_mean]
         return out

@@ -25,7 +25,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from .. import kernels
-from .._compat import ConstantMean, MultivariateNormal, NormalPrior, Positive, ZeroMean
+from .._compat import ConstantMean, Module as _CompatModule, MultivariateNormal, NormalPrior, Positive, ZeroMean
 from ..optim import fit_model_continuation, fit_model_scipy, fit_model_torch
 from ..preprocessing import setlevels
 from ..priors import MollifiedUniformPrior
@@ -119,8 +119,8 @@ class GP_Plus(GPR):
             raise ValueError("calibration_id should be a list where each entry shows the column number in the "
                              "dataset that the calibration parameters are assigned to.")
         # variants outside the accelerated hot path
-        if embedding_type == "probabilistic" or calibration_type == "probabilistic" or len(calibration_id) > 0:
-            raise NotImplementedError("probabilistic embedding / calibration are outside the B200 engine's scope")
+        if calibration_type == "probabilistic" or len(calibration_id) > 0:
+            raise NotImplementedError("calibration parameters are outside the B200 engine's scope")
         if len(separate_embedding) > 0:
             raise NotImplementedError("separate_embedding: the reference only feeds the last latent map into the "
                                       "kernel (models/gp_plus.py:410-437); use the default shared map")
@@ -212,10 +212,20 @@ class GP_Plus(GPR):
             self.zeta.append(zeta)
             self.perm.append(perm)
             self.perm_dict.append(perm_dict)
-            latent_map = FFNN(self, input_size=sum(cat), num_classes=embedding_dim, layers=NN_layers_embedding,
-                              name="latent" + str(cols)).to(dtype=dtype)
-            self.A_matrix.append(latent_map)
-            object.__setattr__(self, "_latent_map", latent_map)
+            if embedding_type == "probabilistic":
+                # variational encoder: each level combination gets a 2-D Gaussian N(mu, L L^T) in the latent space,
+                # sampled once per forward pass with a seeded epsilon (gp_plus.py:347-349, 414-437, 1373-1413);
+                # registered as the sub-module ``A_matrix`` so its weights pack after the kernel parameters
+                if embedding_dim != 2:
+                    raise ValueError("the probabilistic embedding is two-dimensional (gp_plus.py:1387-1412)")
+                self.A_matrix = Variational_Encoder(input_size=sum(cat), num_classes=5, layers=NN_layers_embedding
+                                                    ).to(dtype=dtype)
+                object.__setattr__(self, "_latent_map", None)
+            else:
+                latent_map = FFNN(self, input_size=sum(cat), num_classes=embedding_dim, layers=NN_layers_embedding,
+                                  name="latent" + str(cols)).to(dtype=dtype)
+                self.A_matrix.append(latent_map)
+                object.__setattr__(self, "_latent_map", latent_map)
             strides = np.ones(len(cat), dtype=np.int64)
             for k in range(len(cat) - 2, -1, -1):
                 strides[k] = strides[k + 1] * cat[k + 1]
@@ -303,8 +313,58 @@ class GP_Plus(GPR):
         if self._level_strides is None:
             return None
         dtype = self.covar_module.raw_outputscale.dtype
+        if self.embedding_type == "probabilistic":
+            return self._sampled_latent_tables(dtype) / self._latent_kernel.lengthscale.reshape(-1)[0]
         z = self._latent_map(self.zeta[-1].to(dtype))
         return z / self._latent_kernel.lengthscale.reshape(-1)[0]
+
+    def _latent_passes(self) -> int:
+        """Latent tables averaged into the covariance: ``num_pass_train`` forward passes in training mode,
+        ``num_pass_pred`` in eval mode (gp_plus.py:387-393); 1 for the deterministic map."""
+        if self.embedding_type != "probabilistic" or self._level_strides is None:
+            return 1
+        return max(1, int(self.num_pass_train if self.training else self.num_pass_pred))
+
+    def _sampled_latent_tables(self, dtype) -> torch.Tensor:
+        """[passes, n_combo, 2] latent positions of the probabilistic embedding, one table per forward pass.
+
+        Mirrors gp_plus.py:388-437: the generator is re-seeded with ``seed_number`` at every forward, each pass
+        draws ``epsilon ~ N(0, 1)`` of shape [u, 2] for the u level combinations PRESENT in the training inputs
+        (``torch.unique(one_hot_rows, dim=0)`` order), the encoder turns (one-hot row, epsilon) into a position, and
+        the positions are written into a float32 buffer (``x_raw = torch.zeros(n, 2)``) before they reach the kernel,
+        i.e. rounded to float32 -- kept, with a straight-through gradient.  A private generator is used instead of
+        re-seeding torch's global one."""
+        present = self.__dict__.get("_present_combos")
+        if present is None:
+            lv = self._level_index(self.train_inputs[0], True)
+            rows = self.zeta[-1][np.unique(lv)]
+            uniq = torch.unique(rows, dim=0)  # lexicographic order of the one-hot rows, as the reference gets it
+            # combination index of every unique one-hot row
+            table = {tuple(r.tolist()): i for i, r in enumerate(self.zeta[-1])}
+            present = (uniq, torch.as_tensor([table[tuple(r.tolist())] for r in uniq], dtype=torch.long))
+            self.__dict__["_present_combos"] = present
+        uniq, combo = present
+        gen = torch.Generator().manual_seed(int(self.seed))
+        passes = self._latent_passes()
+        n_combo = self.zeta[-1].shape[0]
+        tables = []
+        for _ in range(passes):
+            eps = torch.normal(mean=0.0, std=1.0, size=[uniq.shape[0], 2], generator=gen)
+            pos = self.A_matrix(uniq.to(dtype), eps)
+            pos = pos + (pos.float().to(pos.dtype) - pos).detach()  # float32 rounding, gradient passes through
+            tables.append(torch.zeros(n_combo, 2, dtype=pos.dtype).index_copy(0, combo, pos))
+        return torch.stack(tables)
+
+    def _check_combos_seen(self, levels: np.ndarray):
+        if self.embedding_type == "probabilistic":
+            seen = set(self.__dict__["_present_combos"][1].tolist()) if "_present_combos" in self.__dict__ else None
+            if seen is None:
+                self._sampled_latent_tables(self.covar_module.raw_outputscale.dtype)
+                seen = set(self.__dict__["_present_combos"][1].tolist())
+            if not set(np.unique(levels).tolist()) <= seen:
+                raise ValueError("probabilistic embedding: a level combination of the prediction inputs does not occur "
+                                 "in the training data (the reference samples latent positions for training "
+                                 "combinations only, gp_plus.py:419-434)")
 
     def _mean_layout(self):
         if self.m_gp == "multiple_constant":
@@ -597,6 +657,8 @@ class GP_Plus(GPR):
             raise RuntimeError("No categorical Variable, No latent positions")
         with torch.no_grad():
             dtype = self.covar_module.raw_outputscale.dtype
+            if self.embedding_type == "probabilistic":
+                return self._sampled_latent_tables(dtype).detach()
             return self._latent_map(self.zeta[-1].to(dtype)).detach()
 
 
@@ -605,6 +667,64 @@ class Linear_MAP(nn.Linear):
 
     def forward(self, input, transform=lambda x: x):
         return F.linear(input, transform(self.weight), self.bias)
+
+
+class Linear_VAE(_CompatModule):
+    """Affine layer of the variational encoder (gp_plus.py:1302-1341): weight / bias registered under
+    ``<name>weight`` / ``<name>bias`` with N(0, 0.2) / N(0, 0.05) priors; evaluated in float64."""
+
+    def __init__(self, in_features: int, out_features: int, bias: bool = True, name=None):
+        super().__init__()
+        self.in_features, self.out_features, self.name = in_features, out_features, str(name)
+        self.register_parameter(self.name + "weight", nn.Parameter(torch.empty((out_features, in_features))))
+        self.register_prior(self.name + "prior_m_weight_fci", NormalPrior(0.0, 0.2), self.name + "weight")
+        if bias:
+            self.register_parameter(self.name + "bias", nn.Parameter(torch.empty(out_features)))
+            self.register_prior(self.name + "prior_m_bias_fci", NormalPrior(0.0, 0.05), self.name + "bias")
+        else:
+            self.register_parameter("bias", None)
+        w = getattr(self, self.name + "weight")
+        nn.init.kaiming_uniform_(w, a=math.sqrt(5))
+        b = getattr(self, self.name + "bias", None)
+        if b is not None:
+            fan_in, _ = nn.init._calculate_fan_in_and_fan_out(w)
+            bound = 1 / math.sqrt(fan_in) if fan_in > 0 else 0
+            nn.init.uniform_(b, -bound, bound)
+
+    def forward(self, input):
+        return F.linear(input.double(), getattr(self, self.name + "weight").double(),
+                        getattr(self, self.name + "bias").double())
+
+
+class Variational_Encoder(_CompatModule):
+    """(one-hot row, epsilon) -> 2-D latent position (gp_plus.py:1373-1413): the network outputs
+    (L22, L21, L11, mu2, mu1) and the position is mu + L epsilon with |.| on the diagonal of L.  With hidden layers the
+    FIRST layer has no activation (as in the reference), the others are tanh."""
+
+    def __init__(self, input_size, num_classes, layers):
+        super().__init__()
+        self.hidden_num = len(layers)
+        if self.hidden_num > 0:
+            self.fci = Linear_VAE(input_size, layers[0], bias=True, name="fci")
+            for i in range(1, self.hidden_num):
+                setattr(self, "h" + str(i), Linear_VAE(layers[i - 1], layers[i], bias=True, name="h" + str(i)))
+            self.fce = Linear_VAE(layers[-1], num_classes, bias=True, name="fce")
+        else:
+            self.fci = Linear_VAE(input_size, num_classes, bias=True, name="fci")
+
+    def forward(self, x, epsilon):
+        if self.hidden_num > 0:
+            x = self.fci(x)
+            for i in range(1, self.hidden_num):
+                x = torch.tanh(getattr(self, "h" + str(i))(x))
+            output = self.fce(x)
+        else:
+            output = self.fci(x)
+        e1, e2 = epsilon[:, 0:1], epsilon[:, 1:2]
+        L22, L21, L11, mu2, mu1 = (output[:, k:k + 1] for k in range(5))
+        x1 = mu1 + 1 * torch.abs(L11) * e1
+        x2 = mu2 + 1 * L21 * e1 + 1 * torch.abs(L22) * e2
+        return torch.cat((x1, x2), 1)
 
 
 class FFNN(nn.Module):

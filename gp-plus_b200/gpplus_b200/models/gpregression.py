@@ -170,6 +170,12 @@ class GPR(Module):
     def _latent_table(self) -> Optional[torch.Tensor]:
         return None
 
+    def _latent_passes(self) -> int:
+        return 1
+
+    def _check_combos_seen(self, levels):
+        return None
+
     def _quant_kernel(self):
         leaves = [k for k in self.covar_module.leaf_kernels() if k.has_lengthscale]
         if len(leaves) != 1:
@@ -199,19 +205,20 @@ class GPR(Module):
         x = self.train_inputs[0]
         qk = self._quant_kernel() if len(self._quant_columns()) > 0 else None
         family = qk.family if qk is not None else _engine.KERNEL_EXPSQ
-        table = self._latent_table()
+        with torch.no_grad():
+            table = self._latent_table()
         n_mean, _ = self._mean_layout()
         n_noise = int(self.likelihood.noise_covar.raw_noise.numel())
         xq = x[:, self._quant_columns()].detach().double().cpu().numpy() if qk is not None else None
         return _engine.Engine(
             xq=xq, y=self.train_targets.detach().double().cpu().numpy(), kernel=family,
-            level_idx=self._level_index(x, True), n_combo=0 if table is None else int(table.shape[0]),
-            dz=0 if table is None else int(table.shape[1]), noise_idx=self._noise_index(x), n_noise=n_noise,
-            mean_idx=self._mean_index(x), n_mean=n_mean, device=dev)
+            level_idx=self._level_index(x, True), n_combo=0 if table is None else int(table.shape[-2]),
+            dz=0 if table is None else int(table.shape[-1]), noise_idx=self._noise_index(x), n_noise=n_noise,
+            mean_idx=self._mean_index(x), n_mean=n_mean, device=dev, n_pass=self._latent_passes())
 
     def _get_engine(self) -> "_engine.Engine":
         dev = get_default_device()
-        if self._engine is not None and self._engine_device == dev:
+        if self._engine is not None and self._engine_device == dev and self._engine.n_pass == self._latent_passes():
             return self._engine
         if self._engine is not None:
             self._engine.close()
@@ -310,8 +317,11 @@ class GPR(Module):
             add_noise = bool(return_std and include_noise)
             if add_noise and isinstance(self.likelihood, Multifidelity_likelihood):
                 self.likelihood.fidel_indices = x[:, -1]
+            levels = self._level_index(xc, False)
+            if levels is not None:
+                self._check_combos_seen(levels)
             mean_sc, var_sc = eng.predict(
-                np.ascontiguousarray(xq), level_idx=self._level_index(xc, False),
+                np.ascontiguousarray(xq), level_idx=levels,
                 noise_idx=self._noise_index(xc) if add_noise else None, mean_idx=self._mean_index(xc),
                 include_noise=add_noise, min_var=settings.min_variance)
             dtype = self.y_std.dtype if self.y_std.dtype.is_floating_point else torch.float64

@@ -324,6 +324,8 @@ def build(model, add_prior: bool, regularization_parameter) -> Optional[FastObje
             raise _Unsupported("weight regularisation")
         if not hasattr(model, "_latent_table") or not hasattr(model, "_mean_layout"):
             raise _Unsupported("not an engine-backed model")
+        if getattr(model, "embedding_type", "deterministic") != "deterministic":
+            raise _Unsupported("probabilistic embedding (sampled latent tables): torch path")
         return FastObjective(model, add_prior)
     except _Unsupported:
         return None

@@ -76,12 +76,15 @@ typedef struct gpp_problem {
     const int32_t* level_idx; /* [n] row of Z per point (perm_dict lookup, gp_plus.py:1085); NULL if dz==0 */
     const int32_t* noise_idx; /* [n] noise group per point (multifidelity.py:105-136); NULL = all 0 */
     const int32_t* mean_idx;  /* [n] mean constant per point, -1 = zero mean (gp_plus.py:529-534); NULL = all 0 */
+    int32_t n_pass;           /* latent tables averaged into K: Sigma = (1/k) sum_p K(Z_p) -- the multi-pass ensemble
+                               * covariance of the probabilistic embedding (gp_plus.py:387-399, 414-461, 474-482);
+                               * 0 or 1 = one deterministic table */
 } gpp_problem;
 
 /* Hyper-parameters in natural form for one evaluation. */
 typedef struct gpp_hyper {
     const double* w;        /* [dq]  distance weights (see GPP_KERNEL_*) */
-    const double* z;        /* [n_combo*dz] latent table Z = zeta_table * A^T (gp_plus.py:436), NULL if dz==0 */
+    const double* z;        /* [n_pass*n_combo*dz] latent table(s) Z = zeta_table * A^T (gp_plus.py:436), NULL if dz==0 */
     double sigma_f2;        /* outputscale = softplus(raw) (gpregression.py:108-111) */
     const double* noise;    /* [n_noise] noise variances lb+exp(raw) (gpregression.py:59) */
     const double* beta;     /* [n_mean]  mean constants, NULL if n_mean==0 */
@@ -98,7 +101,7 @@ typedef struct gpp_mll_result {
     double jitter;          /* diagonal jitter that was needed (0, 1e-8, 1e-7 or 1e-6) */
     double d_sigma_f2;
     double* d_w;            /* [dq] */
-    double* d_z;            /* [n_combo*dz] */
+    double* d_z;            /* [n_pass*n_combo*dz] */
     double* d_noise;        /* [n_noise] */
     double* d_beta;         /* [n_mean] */
 } gpp_mll_result;
@@ -128,8 +131,13 @@ const char* gpp_last_error(void);
 /* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
 long long gpp_launch_count(void);
 
+/* gpp_destroy parks handles of small problems (<= 192 MB of device memory) in a per-process pool and gpp_create
+ * hands a parked handle of the same shape and device back after re-uploading the training data: the multi-start
+ * driver creates dozens of handles per fit and allocation / teardown would otherwise cost more than the fit.
+ * gpp_pool_clear frees every parked handle (GPP_POOL=0 disables parking). */
 int gpp_create(const gpp_problem* problem, int device, gpp_handle** out);
 void gpp_destroy(gpp_handle* h);
+void gpp_pool_clear(void);
 
 /* replaces MLLObjective.fun (optim/mll_scipy.py:112-127) */
 int gpp_mll_grad(gpp_handle* h, const gpp_hyper* hyper, int want_grad, gpp_mll_result* out);

@@ -101,10 +101,13 @@ def covariance(xq1, lvl1, xq2, lvl2, w, z, sf2, kind, mode="expansion", centre=N
     s = sq_dist(xq1 * sw, xq2 * sw, mode, None if centre is None else centre * sw)
     k = quant_corr(s, kind)
     if z is not None and z.numel() > 0:
-        z1 = z[lvl1]
-        z2 = z[lvl2]
-        sz = sq_dist(z1, z2, mode)
-        k = k * torch.exp(-0.5 * sz)  # RBFKernel with lengthscale fixed to 1 (gp_plus.py:223-226)
+        if z.dim() == 3:
+            # multi-pass ensemble (gp_plus.py:387-399, 474-482): Sigma = (1/k) sum_p (K_p + m m^T) - m m^T with one
+            # latent table per pass; the quantitative factor and the mean are common to the passes
+            lat = sum(torch.exp(-0.5 * sq_dist(zp[lvl1], zp[lvl2], mode)) for zp in z) / z.shape[0]
+        else:
+            lat = torch.exp(-0.5 * sq_dist(z[lvl1], z[lvl2], mode))  # RBFKernel, lengthscale 1 (gp_plus.py:223-226)
+        k = k * lat
     return sf2 * k
 
 
@@ -135,7 +138,9 @@ def _hyper_tensors(problem: Dict, hyper: Dict, requires_grad: bool):
     w = _t(hyper["w"]).reshape(dq).clone().requires_grad_(requires_grad)
     z = None
     if dz > 0:
-        z = _t(hyper["z"]).reshape(int(problem["n_combo"]), dz).clone().requires_grad_(requires_grad)
+        n_pass = int(problem.get("n_pass", 1) or 1)
+        shape = (int(problem["n_combo"]), dz) if n_pass <= 1 else (n_pass, int(problem["n_combo"]), dz)
+        z = _t(hyper["z"]).reshape(shape).clone().requires_grad_(requires_grad)
     sf2 = _t(float(hyper["sigma_f2"])).clone().requires_grad_(requires_grad)
     noise = _t(hyper["noise"]).reshape(-1).clone().requires_grad_(requires_grad)
     n_mean = int(problem.get("n_mean", 0))

@@ -50,7 +50,8 @@ def theta_layout(spec: Dict):
     """[(name, shape)] in the reference's ``named_parameters`` order for trainable parameters."""
     out = []
     qual = spec.get("qual_dict", {})
-    if len(qual) > 0:
+    prob = spec.get("embedding_type", "deterministic") == "probabilistic"
+    if len(qual) > 0 and not prob:
         cols = list(qual.keys())
         out.append(("latent" + str(cols), (2, sum(qual.values()))))
     n_noise = list(qual.values())[-1] if spec.get("multiple_noise", False) else 1
@@ -63,6 +64,10 @@ def theta_layout(spec: Dict):
         name = "covar_module.base_kernel.kernels.1.raw_lengthscale" if len(qual) > 0 \
             else "covar_module.base_kernel.raw_lengthscale"
         out.append((name, (1, nq)))
+    if len(qual) > 0 and prob:
+        # Variational_Encoder registered as the sub-module A_matrix after the kernel (gp_plus.py:347-349, 1373-1385)
+        out.append(("A_matrix.fci.fciweight", (5, sum(qual.values()))))
+        out.append(("A_matrix.fci.fcibias", (5,)))
     m_gp = spec.get("m_gp", "single_constant")
     if m_gp == "single_constant":
         out.append(("mean_module.constant", (1,)))
@@ -97,12 +102,30 @@ def neg_log_posterior(spec: Dict, theta: np.ndarray, add_prior: bool = True, the
 
     qcols = list(qual.keys())
     quant_cols = [c for c in range(X.shape[1]) if c not in qcols]
+    prob = spec.get("embedding_type", "deterministic") == "probabilistic"
     parts = []
     if len(qual) > 0:
         zeta, lookup = _one_hot_table(list(qual.values()))
         idx = [lookup[str([int(v) for v in row])] for row in X[:, qcols].tolist()]  # per-row dict lookup
-        A = params["latent" + str(qcols)]
-        parts.append(zeta[idx] @ A.T)  # Linear_MAP, no bias
+        if prob:
+            # gp_plus.py:388-437: generator re-seeded at every forward; per pass epsilon ~ N(0,1) [u, 2] for the u
+            # unique one-hot rows of the inputs (torch.unique order); encoder output (L22, L21, L11, mu2, mu1);
+            # positions copied into a float32 buffer (x_raw) -> float32 rounding with a pass-through gradient
+            rows = zeta[idx]
+            uniq, inverse = torch.unique(rows, dim=0, return_inverse=True)
+            gen = torch.Generator().manual_seed(int(spec.get("seed_number", 1)))
+            W, b = params["A_matrix.fci.fciweight"], params["A_matrix.fci.fcibias"]
+            for _ in range(int(spec.get("num_pass_train", 1))):
+                eps = torch.normal(mean=0.0, std=1.0, size=[uniq.shape[0], 2], generator=gen).to(torch.float64)
+                o = uniq @ W.T + b
+                x1 = o[:, 4:5] + torch.abs(o[:, 2:3]) * eps[:, 0:1]
+                x2 = o[:, 3:4] + o[:, 1:2] * eps[:, 0:1] + torch.abs(o[:, 0:1]) * eps[:, 1:2]
+                pos = torch.cat([x1, x2], 1)
+                pos = pos + (pos.float().double() - pos).detach()
+                parts.append(pos[inverse])
+        else:
+            A = params["latent" + str(qcols)]
+            parts.append(zeta[idx] @ A.T)  # Linear_MAP, no bias
     x_quant = X[:, quant_cols]
 
     # means
@@ -122,8 +145,9 @@ def neg_log_posterior(spec: Dict, theta: np.ndarray, add_prior: bool = True, the
     # kernel tree
     k = torch.ones(n, n, dtype=torch.float64)
     if len(qual) > 0:
-        z = parts[0]
-        k = k * torch.exp(-0.5 * O.sq_dist(z, z, mode))  # RBFKernel, lengthscale 1
+        # one latent table per forward pass; the passes are averaged (gp_plus.py:474-482; the quantitative factor,
+        # the output scale and the mean are the same in every pass)
+        k = k * sum(torch.exp(-0.5 * O.sq_dist(z, z, mode)) for z in parts) / len(parts)  # RBFKernel, lengthscale 1
     if len(quant_cols) > 0:
         raw = params["covar_module.base_kernel.kernels.1.raw_lengthscale" if len(qual) > 0
                      else "covar_module.base_kernel.raw_lengthscale"].reshape(-1)
@@ -168,7 +192,10 @@ def neg_log_posterior(spec: Dict, theta: np.ndarray, add_prior: bool = True, the
             return torch.distributions.Normal(torch.tensor(loc, dtype=torch.float64),
                                               torch.tensor(scale, dtype=torch.float64))
 
-        if len(qual) > 0:
+        if len(qual) > 0 and prob:
+            logp = logp + normal(0.0, 0.2).log_prob(params["A_matrix.fci.fciweight"]).sum()
+            logp = logp + normal(0.0, 0.05).log_prob(params["A_matrix.fci.fcibias"]).sum()
+        elif len(qual) > 0:
             logp = logp + normal(0.0, 1.0).log_prob(params["latent" + str(qcols)]).sum()
         # marginal_log_likelihood adds EVERY registered prior (mll_scipy.py:40-43 has no requires_grad test): with
         # fix_noise the horseshoe term of the frozen raw noise is a constant offset of the objective

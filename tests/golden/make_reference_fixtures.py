@@ -140,6 +140,13 @@ def main_models():
     X, y = borehole_mixed_variables(n=1200, qual_dict=qd, random_state=4)
     Xtr, Xte, ytr, yte = train_test_split_normalizeX(X, y, test_size=0.75, qual_dict=qd)
     model_case("c2_mixed_rough", Xtr, ytr, Xte[:64], {"qual_dict": qd}, single_level_col=0)
+    # probabilistic embedding (variational encoder, seeded epsilon) with one and with three forward passes: the
+    # multi-pass ensemble covariance Sigma = (1/k) sum_p (K_p + m m^T) - m m^T (gp_plus.py:387-399, 414-461, 474-482)
+    model_case("c2_mixed_probabilistic_p1", Xtr[:150], ytr[:150], Xte[:32],
+               {"qual_dict": qd, "embedding_type": "probabilistic"}, single_level_col=0)
+    model_case("c2_mixed_probabilistic_p3", Xtr[:150], ytr[:150], Xte[:32],
+               {"qual_dict": qd, "embedding_type": "probabilistic", "num_pass_train": 3, "num_pass_pred": 3,
+                "quant_correlation_class": "Matern52Kernel"}, single_level_col=0)
     # C3: multi-fidelity wing (Example 03): 4 sources, one noise per source, one mean per source
     set_seed(4)
     X, y = multi_fidelity_wing(n={"0": 50, "1": 100, "2": 100, "3": 100},

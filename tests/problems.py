@@ -2,11 +2,11 @@
 import numpy as np
 
 
-def make_problem(n, dq, kernel, dz=0, n_combo=0, n_noise=1, n_mean=1, seed=0, zero_mean_group=False):
+def make_problem(n, dq, kernel, dz=0, n_combo=0, n_noise=1, n_mean=1, seed=0, zero_mean_group=False, n_pass=1):
     rng = np.random.default_rng(seed)
     xq = rng.standard_normal((n, dq)) if dq > 0 else np.zeros((n, 0))
     p = {"n": n, "dq": dq, "dz": dz, "n_combo": n_combo if dz > 0 else 0, "n_noise": n_noise, "n_mean": n_mean,
-         "kernel": kernel, "xq": xq}
+         "kernel": kernel, "xq": xq, "n_pass": n_pass}
     f = np.zeros(n)
     if dq > 0:
         f = np.sin(xq[:, 0]) + 0.5 * np.cos(2.0 * xq[:, min(1, dq - 1)]) + 0.1 * xq.sum(1)
@@ -37,7 +37,10 @@ def make_hyper(p, seed=1, noise=1e-3, w_scale=0.3):
     h = {"w": w_scale * np.exp(0.5 * rng.standard_normal(p["dq"])),
          "sigma_f2": 0.7 + 0.2 * rng.random(),
          "noise": noise * (1.0 + rng.random(p["n_noise"]))}
-    if p["dz"] > 0:
+    if p["dz"] > 0 and p.get("n_pass", 1) > 1:
+        base = 0.8 * rng.standard_normal((1, p["n_combo"], p["dz"]))
+        h["z"] = base + 0.3 * rng.standard_normal((p["n_pass"], p["n_combo"], p["dz"]))
+    elif p["dz"] > 0:
         h["z"] = 0.8 * rng.standard_normal((p["n_combo"], p["dz"]))
     else:
         h["z"] = None
@@ -62,4 +65,4 @@ def make_candidates(p, m, seed=2):
 def engine_kwargs(p, device=0):
     return dict(xq=p["xq"], y=p["y"], kernel=p["kernel"], level_idx=p["level_idx"], n_combo=p["n_combo"],
                 dz=p["dz"], noise_idx=p["noise_idx"], n_noise=p["n_noise"], mean_idx=p["mean_idx"],
-                n_mean=p["n_mean"], device=device)
+                n_mean=p["n_mean"], device=device, n_pass=p.get("n_pass", 1))

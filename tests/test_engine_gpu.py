@@ -273,3 +273,67 @@ def test_schedule_variants_are_bitwise_identical(n, monkeypatch):
     out, li, ki = results[3]
     assert abs(out["nll"] - ref[0]["nll"]) <= 1e-11 * abs(ref[0]["nll"])
     assert np.max(np.abs(ki - ref[2])) <= 1e-9 * np.max(np.abs(ref[2]))
+
+
+def test_recycled_handles_give_the_results_of_fresh_ones():
+    """gpp_destroy parks small handles, gpp_create hands them back for a problem of the same shape: the recycled
+    handle (captured CUDA graphs included) must evaluate the NEW training set, bit for bit like a fresh handle."""
+    from gpplus_b200 import _engine as E
+    E.pool_clear()
+    pa = make_problem(n=300, dq=5, kernel=2, dz=2, n_combo=6, n_noise=2, n_mean=2, seed=41)
+    pb = make_problem(n=300, dq=5, kernel=2, dz=2, n_combo=6, n_noise=2, n_mean=2, seed=42)
+    ha, hb = make_hyper(pa, seed=43), make_hyper(pb, seed=44)
+    fresh_b = E.Engine(**engine_kwargs(pb))
+    want = fresh_b.mll_grad(hb, want_grad=True)
+    cand = make_candidates(pb, 40, seed=45)
+    fresh_b.factorize(hb)
+    mu_w, var_w = fresh_b.predict(cand["xq"], level_idx=cand["level_idx"], noise_idx=cand["noise_idx"],
+                                  mean_idx=cand["mean_idx"], include_noise=True)
+    first = E.Engine(**engine_kwargs(pa))
+    first.mll_grad(ha, want_grad=True)   # captures the graphs on problem A
+    first.mll_grad(ha, want_grad=False)
+    first.close()                        # parked
+    again = E.Engine(**engine_kwargs(pb))  # recycled: same shape, new data
+    got = again.mll_grad(hb, want_grad=True)
+    assert got["nll"] == want["nll"]
+    for k in ("d_w", "d_z", "d_noise", "d_beta"):
+        assert np.array_equal(got[k], want[k]), k
+    again.factorize(hb)
+    mu, var = again.predict(cand["xq"], level_idx=cand["level_idx"], noise_idx=cand["noise_idx"],
+                            mean_idx=cand["mean_idx"], include_noise=True)
+    assert np.array_equal(mu, mu_w) and np.array_equal(var, var_w)
+    assert again.stats()["evaluations"] == 2  # counters restart with the new problem
+    again.close()
+    fresh_b.close()
+    E.pool_clear()
+
+
+@pytest.mark.parametrize("kernel,n,n_pass", [(0, 300, 3), (2, 517, 5), (1, 130, 2)])
+def test_multi_pass_ensemble_covariance_matches_oracle(kernel, n, n_pass):
+    """Multi-pass ensemble covariance of the probabilistic embedding (gp_plus.py:387-399, 474-482):
+    K = (1/k) sum_p K(Z_p) over k latent tables -- dense K, NLL, every gradient (one block of d_z per table) and
+    predictions against the CPU oracle."""
+    from gpplus_b200 import _engine as E
+    from oracle import gp_oracle as O
+    p = make_problem(n=n, dq=4, kernel=kernel, dz=2, n_combo=7, n_noise=2, n_mean=2, seed=60 + n_pass, n_pass=n_pass)
+    h = make_hyper(p, seed=70 + n_pass)
+    eng = E.Engine(**engine_kwargs(p))
+    try:
+        ref = O.mll(p, h, want_grad=True, return_mats=True)
+        K = eng.covariance(h)
+        assert np.max(np.abs(K - ref["K"])) <= 1e-13
+        out = eng.mll_grad(h, want_grad=True)
+        assert abs(out["nll"] - ref["nll"]) <= 1e-9 * abs(ref["nll"])
+        assert out["d_z"].shape == (n_pass, 7, 2)
+        for k in ("d_w", "d_z", "d_noise", "d_beta"):
+            err = np.max(np.abs(out[k] - ref[k])) / max(1e-300, np.max(np.abs(ref[k])))
+            assert err < 1e-8, (k, err)
+        assert abs(out["d_sigma_f2"] - ref["d_sigma_f2"]) <= 1e-8 * abs(ref["d_sigma_f2"])
+        cand = make_candidates(p, 200, seed=80)
+        eng.factorize(h)
+        mu, var = eng.predict(cand["xq"], level_idx=cand["level_idx"], noise_idx=cand["noise_idx"],
+                              mean_idx=cand["mean_idx"], include_noise=True)
+        mu_r, var_r = O.predict(p, h, cand, include_noise=True)
+        assert np.max(np.abs(mu - mu_r)) <= 1e-9 and np.max(np.abs(var - var_r)) <= 1e-9
+    finally:
+        eng.close()

@@ -36,6 +36,19 @@ TOL_GRAD = 1e-8     # relative to the gradient's max-norm
 TOL_POST = 2e-8
 
 
+def post_scale(z, k):
+    """Magnitude the posterior tolerance refers to: |data term| + |prior term| (their sum can cancel)."""
+    nll, post = float(z["f_f64_nll"][k]), float(z["f_f64_post"][k])
+    return abs(nll) + abs(post - nll)
+
+
+def grad_tol(kw):
+    """Gradient tolerance relative to the gradient's max-norm.  The probabilistic embedding of the reference copies
+    the sampled latent positions into a float32 buffer (gp_plus.py:418, 435-436), so the gradient that flows back to
+    the encoder weights is rounded to float32 there: its own gradient is float32-accurate only."""
+    return 1e-6 if kw.get("embedding_type") == "probabilistic" else TOL_GRAD
+
+
 def load_case(name):
     z = np.load(os.path.join(GOLD, "ref_%s.npz" % name))
     meta = json.loads(bytes(z["meta_json"]).decode())
@@ -48,7 +61,8 @@ def load_case(name):
 def oracle_spec(z, kw):
     spec = {"X": z["Xtr"], "y": z["ytr"], "qual_dict": kw.get("qual_dict", {}),
             "kernel": kw.get("quant_correlation_class", "Rough_RBF")}
-    for k in ("multiple_noise", "m_gp", "m_gp_ref", "fix_noise", "fix_noise_val", "lb_noise", "interval_score"):
+    for k in ("multiple_noise", "m_gp", "m_gp_ref", "fix_noise", "fix_noise_val", "lb_noise", "interval_score",
+              "embedding_type", "num_pass_train", "num_pass_pred", "seed_number"):
         if k in kw:
             spec[k] = kw[k]
     return spec
@@ -76,11 +90,11 @@ def test_oracle_matches_the_reference_objective(name):
         f, g = GO.neg_log_posterior(spec, th, add_prior=False)
         fr, gr = float(z["f_f64_nll"][k]), z["g_f64_nll"][k]
         assert abs(f - fr) <= TOL_NLL * abs(fr), (name, k, f, fr)
-        assert np.max(np.abs(g - gr)) <= TOL_GRAD * np.max(np.abs(gr)), (name, k)
+        assert np.max(np.abs(g - gr)) <= grad_tol(kw) * np.max(np.abs(gr)), (name, k)
         f, g = GO.neg_log_posterior(spec, th, add_prior=True)
         fr, gr = float(z["f_f64_post"][k]), z["g_f64_post"][k]
-        assert abs(f - fr) <= TOL_POST * abs(fr), (name, k, f, fr)
-        assert np.max(np.abs(g - gr)) <= 1e-7 * np.max(np.abs(gr)), (name, k)
+        assert abs(f - fr) <= TOL_POST * post_scale(z, k), (name, k, f, fr)
+        assert np.max(np.abs(g - gr)) <= max(1e-7, grad_tol(kw)) * np.max(np.abs(gr)), (name, k)
 
 
 @pytest.mark.parametrize("name", MODEL_CASES)
@@ -107,8 +121,9 @@ def test_product_host_logic_matches_the_reference(name):
     assert [n for n, *_ in m.named_priors()] == meta["prior_names"]
     theta0 = obj.pack_parameters()
     # everything but the randomly initialised latent map must start where the reference starts
-    lat = sum(int(np.prod(s)) for n, s in zip(meta["param_names"], meta["param_shapes"]) if n.startswith("latent"))
-    np.testing.assert_allclose(theta0[lat:], z["theta_init"][lat:], rtol=0, atol=1e-7)
+    random_init = np.concatenate([np.full(int(np.prod(s)), n.startswith("latent") or n.startswith("A_matrix"))
+                                  for n, s in zip(meta["param_names"], meta["param_shapes"])])
+    np.testing.assert_allclose(theta0[~random_init], z["theta_init"][~random_init], rtol=0, atol=1e-7)
     lo, hi = get_bounds(obj, theta0)
     np.testing.assert_array_equal(lo, z["bounds_lo"])
     np.testing.assert_array_equal(hi, z["bounds_hi"])
@@ -137,8 +152,9 @@ def test_product_natural_parameters_reproduce_the_reference_through_the_oracle(n
         with torch.no_grad():
             w, zt, sf2, noise, beta = m._natural()
         n_mean, _ = m._mean_layout()
-        prob = {"n": x.shape[0], "dq": len(cols), "dz": 0 if zt.numel() == 0 else int(zt.shape[1]),
-                "n_combo": 0 if zt.numel() == 0 else int(zt.shape[0]), "n_noise": int(noise.numel()), "n_mean": n_mean,
+        prob = {"n": x.shape[0], "dq": len(cols), "dz": 0 if zt.numel() == 0 else int(zt.shape[-1]),
+                "n_combo": 0 if zt.numel() == 0 else int(zt.shape[-2]), "n_pass": int(zt.shape[0]) if zt.dim() == 3 else 1,
+                "n_noise": int(noise.numel()), "n_mean": n_mean,
                 "kernel": qk.family if qk is not None else 0, "xq": x[:, cols].double().numpy(),
                 "y": m.train_targets.double().numpy(), "level_idx": m._level_index(x, True),
                 "noise_idx": m._noise_index(x), "mean_idx": m._mean_index(x)}
