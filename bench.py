@@ -313,7 +313,7 @@ def run_ours(args):
         t_init.append(eng.timings()["total"])
     per_draw, retried = [], []
     sa = eng.stats()
-    for k in range(1, 1 + W.N_PRIOR_DRAWS):
+    for k in range(1, 1 + (0 if args.no_prior_sweep else W.N_PRIOR_DRAWS)):
         s_before = eng.stats()["jitter_retries"]
         tq = time.time()
         try:
@@ -327,7 +327,7 @@ def run_ours(args):
     sb = eng.stats()
     clean = [m for m, _ in per_draw]
     n_retry = sum(r for _, r in retried)
-    prior_draws = {
+    prior_draws = None if args.no_prior_sweep else {
         "n": W.N_PRIOR_DRAWS, "median_ms": statistics.median(clean) if clean else None,
         "mean_ms": sum(clean) / len(clean) if clean else None, "draws_needing_jitter": len(retried),
         "retries": int(sb["jitter_retries"] - sa["jitter_retries"]), "early_outs": int(sb["early_outs"] - sa["early_outs"]),
@@ -679,6 +679,8 @@ def main():
     ap.add_argument("--no-extras", action="store_true",
                     help="mll workload: skip extra.fit_c2 / extra.acq_c5 (the sharded workloads of the metric's second half)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="mll workload: skip the full-size CPU oracle evaluation")
+    ap.add_argument("--no-prior-sweep", action="store_true",
+                    help="mll workload: skip the untimed sweep over all 65 prior draws (profiling runs)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours" and args.workload == "mll":
         args.warmup = 3

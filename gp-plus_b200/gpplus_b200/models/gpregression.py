@@ -199,9 +199,8 @@ class GPR(Module):
     def _mean_index(self, x: torch.Tensor) -> Optional[np.ndarray]:
         return None
 
-    def _new_engine(self, dev: int) -> "_engine.Engine":
-        """A fresh engine handle holding this model's training set on GPU ``dev`` (not cached: the lock-step
-        multi-start driver keeps one handle per in-flight restart)."""
+    def _engine_kwargs(self, dev: int) -> dict:
+        """Constructor arguments of an engine handle holding this model's training set on GPU ``dev``."""
         x = self.train_inputs[0]
         qk = self._quant_kernel() if len(self._quant_columns()) > 0 else None
         family = qk.family if qk is not None else _engine.KERNEL_EXPSQ
@@ -210,11 +209,16 @@ class GPR(Module):
         n_mean, _ = self._mean_layout()
         n_noise = int(self.likelihood.noise_covar.raw_noise.numel())
         xq = x[:, self._quant_columns()].detach().double().cpu().numpy() if qk is not None else None
-        return _engine.Engine(
+        return dict(
             xq=xq, y=self.train_targets.detach().double().cpu().numpy(), kernel=family,
             level_idx=self._level_index(x, True), n_combo=0 if table is None else int(table.shape[-2]),
             dz=0 if table is None else int(table.shape[-1]), noise_idx=self._noise_index(x), n_noise=n_noise,
             mean_idx=self._mean_index(x), n_mean=n_mean, device=dev, n_pass=self._latent_passes())
+
+    def _new_engine(self, dev: int, kwargs: Optional[dict] = None) -> "_engine.Engine":
+        """A fresh engine handle holding this model's training set on GPU ``dev`` (not cached: the lock-step
+        multi-start driver keeps one handle per in-flight restart and passes the same ``kwargs`` to all of them)."""
+        return _engine.Engine(**(kwargs if kwargs is not None else self._engine_kwargs(dev)))
 
     def _get_engine(self) -> "_engine.Engine":
         dev = get_default_device()

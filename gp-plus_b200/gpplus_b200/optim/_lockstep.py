@@ -160,14 +160,15 @@ def run_lockstep(likobj, theta0_list: List[np.ndarray], work, options: Dict, lo:
             results[i] = chain.result()
 
     try:
+        # every handle first (with the GPU idle), then the first evaluation of every slot
+        t0 = time.time()
+        kwargs = model._engine_kwargs(device)
         for _ in range(n_slots):
-            i_first = None
-            t0 = time.time()
-            eng = model._new_engine(device)
+            eng = model._new_engine(device, kwargs)
             eng.set_theta_layout(spec)
-            t_setup += time.time() - t0
-            slot = [eng, None, i_first]
-            slots.append(slot)
+            slots.append([eng, None, None])
+        t_setup = time.time() - t0
+        for slot in slots:
             if not start(slot):
                 break
         active = [s for s in slots if s[1] is not None]

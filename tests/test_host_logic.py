@@ -88,7 +88,9 @@ def test_unsupported_variants_raise_instead_of_silently_differing():
     X = torch.randn(20, 3, dtype=torch.float64)
     y = torch.randn(20, dtype=torch.float64)
     with pytest.raises(NotImplementedError):
-        GP_Plus(X, y, embedding_type="probabilistic")
+        GP_Plus(X, y, calibration_type="probabilistic")
+    with pytest.raises(NotImplementedError):
+        GP_Plus(X, y, calibration_id=[1])
     with pytest.raises(NotImplementedError):
         GP_Plus(X, y, m_gp="single_polynomial-d2")
     with pytest.raises(RuntimeError):

@@ -59,7 +59,7 @@ def test_engine_predictions_match_the_reference(name):
             assert np.max(np.abs(mu.numpy() - z["pred_mean_" + tag])) <= 1e-7 * span, (name, tag)
             assert np.max(np.abs(sd.numpy() - z["pred_std_" + tag])) <= 1e-6 * span, (name, tag)
         if "single_levels" in z.files:
-            col = {"c2_mixed_rough": 0}.get(name, Xte.shape[1] - 1)
+            col = 0 if name.startswith("c2_") else Xte.shape[1] - 1
             for k, v in enumerate(z["single_levels"]):
                 rows = Xte[Xte[:, col] == v]
                 mu, sd = m.predict(rows.clone(), return_std=True, include_noise=True)
