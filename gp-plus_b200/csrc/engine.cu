@@ -278,9 +278,10 @@ extern "C" int gpp_create(const gpp_problem* p, int device, gpp_handle** out) {
     }
     if (device < 0 || device >= ndev) ARG_FAIL("gpp_create: bad device index");
     CK(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) {
+    // (cudaGetDeviceProperties costs milliseconds per call; the lock-step driver creates dozens of handles per fit)
+    int cc_major = 0;
+    CK(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device));
+    if (cc_major < 10) {
         g_err = "gpp_create: built for sm_100a (B200); device compute capability is too old";
         return GPP_ERR_CUDA;
     }
@@ -355,8 +356,17 @@ extern "C" int gpp_create(const gpp_problem* p, int device, gpp_handle** out) {
     }
     for (int i = 0; i < EV_COUNT; i++) CKH(cudaEventCreate(&h->ev[i]));
     CKH(cudaEventCreateWithFlags(&h->ev_info, cudaEventDisableTiming));
-    CKH(chol_set_attributes());
-    CKH(cov_set_attributes());
+    {
+        // dynamic shared-memory limits of the kernels: once per device and process
+        static std::mutex mu;
+        static bool done[64] = {false};
+        std::lock_guard<std::mutex> lk(mu);
+        if (device >= 64 || !done[device]) {
+            CKH(chol_set_attributes());
+            CKH(cov_set_attributes());
+            if (device < 64) done[device] = true;
+        }
+    }
     {
         // development switches (defaults are the production configuration)
         const char* e;
