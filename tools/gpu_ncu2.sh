@@ -40,3 +40,8 @@ for i in range(12):
 print("cuBLAS (torch.matmul f64) 8192^3: %.3f ms = %.2f TFLOP/s" % (best, 2 * 8192 ** 3 / best / 1e9))
 PY
 cat gpurun_out/r02_probe_dgemm.log
+# the latency-bound small-N evaluation (n=500): kernel-by-kernel launch list with graph replay off
+GPP_GRAPH=0 timeout 300 python tools/small_eval_probe.py > gpurun_out/small_eval_probe.log 2>&1; cat gpurun_out/small_eval_probe.log | tail -4
+LS=$(grep "eval 0" gpurun_out/small_eval_probe.log | sed 's/.*so far //')
+GPP_GRAPH=0 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s $((2*LS)) -c $LS --csv --log-file gpurun_out/r02_launches_n500.csv python tools/small_eval_probe.py > gpurun_out/ncu_small.log 2>&1
+python tools/launch_summary.py gpurun_out/r02_launches_n500.csv
