@@ -608,14 +608,23 @@ def acq_core(args, world, rank, local, steps):
             import torch.distributed as dist
             dist.barrier()
 
-    # end-to-end arm: candidate table in HOST memory (ordering, level lookup, H2D, scoring, arg-max over ranks)
-    e2e_times = []
+    # end-to-end arm: candidate table in HOST memory (ordering, level lookup, H2D, scoring, arg-max over ranks);
+    # timed from PINNED host memory (the bench contract's e2e definition) and from a pageable numpy array
+    table_pinned = torch.from_numpy(table).pin_memory()
+    acquisition_table_argmax(model, table_pinned, best, costs, maximize=False)
+    e2e_times, pageable_times = [], []
     for _ in range(max(1, steps)):
         sync_all()
         t0 = time.time()
-        score, idx, order = acquisition_table_argmax(model, table, best, costs, maximize=False)
+        score_p, idx_p, order_p = acquisition_table_argmax(model, table, best, costs, maximize=False)
+        sync_all()
+        pageable_times.append(time.time() - t0)
+        sync_all()
+        t0 = time.time()
+        score, idx, order = acquisition_table_argmax(model, table_pinned, best, costs, maximize=False)
         sync_all()
         e2e_times.append(time.time() - t0)
+    assert idx_p == idx and score_p == score, "pinned and pageable tables disagree"
     # device-resident arm: this rank's chunk prepared once and already in HBM when the timed region starts
     prep = to_device(prepare_candidate_table(model, table, 5), local)
     score_prepared(model, prep, best, costs, maximize=False)
@@ -627,11 +636,11 @@ def acq_core(args, world, rank, local, steps):
         sync_all()
         dev_times.append(time.time() - t0)
     assert idx_d == idx and score_d == score, "device-resident and host paths disagree"
-    both = torch.tensor([min(e2e_times), min(dev_times)], dtype=torch.float64, device="cuda")
+    both = torch.tensor([min(e2e_times), min(dev_times), min(pageable_times)], dtype=torch.float64, device="cuda")
     if world > 1:
         import torch.distributed as dist
         dist.all_reduce(both, op=dist.ReduceOp.MAX)
-    dt_e2e, dt_dev = float(both[0]), float(both[1])
+    dt_e2e, dt_dev, dt_pageable = float(both[0]), float(both[1]), float(both[2])
     n_tr = int(U.shape[0])
     model.release_engine()
     return {
@@ -641,9 +650,11 @@ def acq_core(args, world, rank, local, steps):
         "config": {"workload": "MFBO borehole, n_train=%d, 5 sources, %d Sobol candidates split in contiguous "
                                "chunks over the ranks; value: chunks resident in HBM" % (n_tr, M)},
         "e2e": {"value": M / dt_e2e, "unit": "candidates/s", "ms_per_step": 1e3 * dt_e2e,
-                "h2d_bytes_per_step": int(M * (8 * 8 + 4 + 4)), "d2h_bytes_per_step": 16,
-                "api": "bayesian_optimizations.acquisition_table_argmax(model, table) from HOST memory: "
-                       "source-major ordering, level lookup, H2D, fused predict+AF+arg-max, arg-max over ranks"},
+                "h2d_bytes_per_step": int(M * 9 * 8), "d2h_bytes_per_step": 16,
+                "from_pageable_numpy_ms": 1e3 * dt_pageable,
+                "api": "bayesian_optimizations.acquisition_table_argmax(model, table) with the table in PINNED host "
+                       "memory: H2D of the whole table, source-major ordering and level lookup on the device, fused "
+                       "predict+AF+arg-max, arg-max over ranks"},
         "best": {"score": score, "index": int(idx), "table_row": int(order[int(idx)])}}
 
 
