@@ -30,7 +30,7 @@ constexpr int LLD = 132;   // smem leading dimension: 132 = 4 (mod 16) keeps eve
 constexpr int TLD = 36;    // per-warp scratch leading dimension (same residue)
 constexpr int PANEL_BLOCKS = 4;   // leaf-level panel: in-panel updates run at K = 128
 constexpr int PANEL_BASE = 2;      // widest piece factored with K = 128 in-panel updates (the recursion stops here)
-inline int g_panel_blocks = 0;     // look-ahead panel width in 128-columns; 0 = by size (8 from N = 12288, else 4)
+inline int g_panel_blocks = 0;     // look-ahead panel width in 128-columns; 0 = by size (12 from N = 12288, else 4)
 constexpr unsigned FULL = 0xffffffffu;
 
 // C(32x32) += A(32x32) * B(32x32) by one warp on DMMA; A(r,k) and B(k,n) are element getters.
@@ -685,8 +685,9 @@ inline int trtri_split_point(int T);
 inline cudaError_t potrf_lookahead(double* A, double* M, int ld, int T, double* logdet_part, int* info,
                                    cudaStream_t st, CholLookahead& la, double* X = nullptr) {
     // K of the trailing update: wide panels only pay off when the trailing matrix is large (measured:
-    // N = 16384 59.0 -> 56.6 ms with 8, N = 8192 12.3 -> 12.8 ms)
-    const int PB = g_panel_blocks > 0 ? g_panel_blocks : (T >= 96 ? 8 : 4);
+    // N = 16384 59.0 -> 56.6 ms with 8, N = 8192 12.3 -> 12.8 ms; round 2, whole evaluation at N = 16384:
+    // 139.3 ms with 8, 138.4 with 12, 138.6 with 16)
+    const int PB = g_panel_blocks > 0 ? g_panel_blocks : (T >= 96 ? 12 : 4);
     const int NP = (T + PB - 1) / PB;
     if (NP > la.panels) return cudaErrorInvalidValue;
     const bool deep = g_lookahead_depth >= 2;

@@ -52,6 +52,9 @@ constexpr int GEMM_SMEM_BYTES = GemmCfg<128>::SMEM_BYTES;  // 163840
 
 // CTA shape used by launch_gemm (process-wide; 128 or 64)
 inline int g_gemm_bm = 64;
+constexpr int GEMM_NUM_SMS = 148;   // B200
+inline int g_gemm_stagger = 10;     // phase shift of the two resident CTAs of an SM in tenths of half a tile time
+                                    // (GPP_STAGGER; 0 = off): potrf alone 53.4 -> 52.4 ms at N = 16384
 
 enum KSel { KSEL_CONST = 0, KSEL_TI = 1, KSEL_TJ = 2 };
 enum TileMap { MAP_RECT = 0, MAP_TRI = 1 };
@@ -78,6 +81,7 @@ struct GemmOp {
     int total_ctas;              // set by launch_gemm: work items along x; CTAs stride over them (persistent when
                                  // the grid is smaller than this)
     int max_ctas;                // 0 = one CTA per work item; otherwise cap on gridDim.x (leaves SMs to other streams)
+    int stagger_ns;              // > 0: the second resident CTA of every SM starts this many ns late (see launch_gemm)
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -130,6 +134,14 @@ __global__ void __launch_bounds__(GemmCfg<BM>::THREADS, GemmCfg<BM>::MIN_CTAS) d
     const int tid = threadIdx.x;
     const int z = blockIdx.y;
     const int tm = (z == (int)gridDim.y - 1) ? op.tiles_m_last : op.tiles_m;
+    if (op.stagger_ns > 0 && blockIdx.x >= GEMM_NUM_SMS && blockIdx.x < 2 * GEMM_NUM_SMS) {
+        // Two CTAs share an SM so that one computes while the other is in its prologue / epilogue -- which only works
+        // if they are out of phase.  With a uniform K range every tile takes the same time, the two CTAs that start
+        // together on an SM stay in lock step for the whole launch and reach their epilogues simultaneously.  Delaying
+        // the CTAs that fill the second slot of every SM by half a tile time once puts the pair (and every CTA that
+        // later inherits one of the two slots) out of phase.
+        for (int w = op.stagger_ns; w > 0; w -= 1000) __nanosleep(w > 1000 ? 1000 : w);
+    }
   for (int work = blockIdx.x; work < op.total_ctas; work += gridDim.x) {
     const int half = (SPLIT == 1) ? 0 : (work % SPLIT);
     const int tile_id = (SPLIT == 1) ? work : (work / SPLIT);
@@ -318,6 +330,13 @@ inline cudaError_t launch_gemm(const GemmOp& op, bool a_kc, bool b_kc, int nbatc
     else nt = op.tiles_m * op.tiles_n;
     if (nt <= 0 || nbatch <= 0) return cudaSuccess;
     count_launch();
+    if (g_gemm_bm == 64 && g_gemm_stagger > 0 && nbatch == 1 && op.klo_sel == KSEL_CONST && op.khi_sel == KSEL_CONST &&
+        2 * nt >= 16 * GEMM_NUM_SMS && op.max_ctas == 0) {
+        // uniform K, at least eight waves: half a tile time = (khi - klo) * 8 chunks * ~2.2 us per chunk / 2
+        GemmOp o2 = op;
+        o2.stagger_ns = (op.khi_c - op.klo_c) * 8 * 11 * g_gemm_stagger * 10;
+        return launch_gemm_bm<64>(o2, a_kc, b_kc, nt, nbatch, st);
+    }
     if (g_gemm_bm == 64) return launch_gemm_bm<64>(op, a_kc, b_kc, nt, nbatch, st);
     return launch_gemm_bm<128>(op, a_kc, b_kc, nt, nbatch, st);
 }

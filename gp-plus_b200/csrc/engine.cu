@@ -374,6 +374,7 @@ extern "C" int gpp_create(const gpp_problem* p, int device, gpp_handle** out) {
         if ((e = getenv("GPP_PANEL")) != nullptr) g_panel_blocks = atoi(e);
         if ((e = getenv("GPP_OVERLAP_INV")) != nullptr) g_overlap_inverse = atoi(e);
         if ((e = getenv("GPP_GEMM_BM")) != nullptr) g_gemm_bm = atoi(e) == 64 ? 64 : 128;
+        if ((e = getenv("GPP_STAGGER")) != nullptr) g_gemm_stagger = atoi(e);
         h->use_graph = h->T <= 16;  // N <= 2048: an evaluation is a chain of ~25-100 tiny launches
         if ((e = getenv("GPP_GRAPH")) != nullptr) h->use_graph = atoi(e) != 0;
         if ((e = getenv("GPP_EARLY_OUT")) != nullptr) h->early_out = atoi(e) != 0;
