@@ -63,7 +63,7 @@ struct gpp_handle {
     int hyp_len = 0;
     double sf2 = 0.0;
     // per-evaluation point panels
-    double *xs = nullptr, *nrm = nullptr, *zpt = nullptr, *r = nullptr, *diag_add = nullptr;
+    double *xs = nullptr, *xst = nullptr, *nrm = nullptr, *zpt = nullptr, *r = nullptr, *diag_add = nullptr;
     double *v = nullptr, *alpha = nullptr, *part = nullptr;
     // N x N work matrices
     double *A = nullptr, *M = nullptr, *S = nullptr;
@@ -395,7 +395,7 @@ extern "C" int gpp_create(const gpp_problem* p, int device, gpp_handle** out) {
         const size_t D = sizeof(double), I = sizeof(int);
         const size_t o_xq = take(D * n * h->dq), o_y = take(D * n), o_centre = take(D * std::max(h->dq, 1));
         const size_t o_lvl = take(I * n), o_nidx = take(I * n), o_midx = take(I * n);
-        const size_t o_hyp = take(D * h->hyp_len), o_xs = take(D * np * h->dqp), o_nrm = take(D * np);
+        const size_t o_hyp = take(D * h->hyp_len), o_xs = take(D * np * h->dqp), o_xst = take(D * np * h->dqp), o_nrm = take(D * np);
         const size_t o_zpt = take(D * h->n_pass * np * ZP), o_r = take(D * np), o_da = take(D * np), o_v = take(D * np);
         const size_t o_alpha = take(D * np), o_part = take(D * T * np);
         const size_t o_A = take(D * np * np), o_M = take(D * np * np), o_S = take(D * np * np);
@@ -411,6 +411,7 @@ extern "C" int gpp_create(const gpp_problem* p, int device, gpp_handle** out) {
         h->centre = (double*)(base + o_centre);
         h->hyp = (double*)(base + o_hyp);
         h->xs = (double*)(base + o_xs);
+        h->xst = (double*)(base + o_xst);
         h->nrm = (double*)(base + o_nrm);
         h->zpt = (double*)(base + o_zpt);
         h->r = (double*)(base + o_r);
@@ -518,6 +519,7 @@ static int stage_prep(gpp_handle* h) {
     pa.n_combo = h->n_combo;
     pa.n_pass = h->n_pass;
     pa.xs = h->xs;
+    pa.xst = h->xst;
     pa.nrm = h->nrm;
     pa.zpt = h->zpt;
     const int nb = (int)((h->np + 255) / 256);
@@ -581,7 +583,7 @@ static int stage_inverse_solve(gpp_handle* h) {
     trmv_lower_kernel<<<(int)(h->np / 8), 256, 0, h->st>>>(h->M, h->np, h->r, (int)h->np, h->v);
     CK(cudaGetLastError());
     count_launch();
-    trmv_lower_t_part_kernel<<<h->T * (h->T + 1) / 2, 128, 0, h->st>>>(h->M, h->np, h->v, (int)h->np, h->part);
+    trmv_lower_t_part_kernel<<<h->T * (h->T + 1) / 2, 512, 0, h->st>>>(h->M, h->np, h->v, (int)h->np, h->part);
     CK(cudaGetLastError());
     count_launch();
     trmv_lower_t_reduce_kernel<<<(int)((h->np + 255) / 256), 256, 0, h->st>>>(h->part, (int)h->np, h->T, h->alpha);
@@ -596,7 +598,7 @@ static int stage_grad(gpp_handle* h) {
     mark(h, EV_LAUUM);
     GradArgs ga;
     memset(&ga, 0, sizeof(ga));
-    ga.xs = h->xs;
+    ga.xst = h->xst;
     ga.nrm = h->nrm;
     ga.alpha = h->alpha;
     ga.Kinv = h->S;
@@ -1155,6 +1157,7 @@ static int predict_impl(gpp_handle* h, long long m, const double* xq, const int3
         pa.n_combo = h->n_combo;
         pa.n_pass = h->n_pass;
         pa.xs = h->c_xs;
+        pa.xst = nullptr;
         pa.nrm = h->c_nrm;
         pa.zpt = h->c_zpt;
         prep_points_kernel<<<(int)((mcp + 255) / 256), 256, 0, h->st>>>(pa);

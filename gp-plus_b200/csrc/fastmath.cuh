@@ -73,4 +73,29 @@ GPP_FM_HD double exp_nonpos(double x) {
 #endif
 }
 
+#if defined(__CUDACC__)
+// Device form used by the tile kernels: same arithmetic, the clamp at -708 done on the high word (x <= 0, so a larger
+// magnitude is a larger unsigned high word; 0xC0862000 is the high word of -708.0) instead of fmax(): one ISETP + two
+// SEL, nothing on the FP64 pipe.
+__device__ __forceinline__ double exp_nonpos_dev(double x) {
+    const double L2E = 1.4426950408889634074;
+    const double LN2_HI = 6.93147180369123816490e-01;
+    const double LN2_LO = 1.90821492927058770002e-10;
+    const double SHIFT = 6755399441055744.0;
+    if ((unsigned)__double2hiint(x) > 0xC0862000u) x = -708.0;
+    const double t = fma(x, L2E, SHIFT);
+    const double nd = t - SHIFT;
+    double r = fma(nd, -LN2_HI, x);
+    r = fma(nd, -LN2_LO, r);
+    const double* c = c_exp_taylor_dev;
+    double p = c[0];
+#pragma unroll
+    for (int k = 1; k < 12; k++) p = fma(p, r, c[k]);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const int n = __double2loint(t);
+    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+}
+#endif
+
 }  // namespace gpp

@@ -30,30 +30,42 @@ __global__ void __launch_bounds__(256) trmv_lower_kernel(const double* M, long l
     if (lane == 0) v[row] = s;
 }
 
-// part[tb][j] = sum_{i in row block tb, i >= j} M[i][j] v[i]; grid = lower (tb, cb) block pairs, 128 threads
-__global__ void __launch_bounds__(128) trmv_lower_t_part_kernel(const double* M, long long ld, const double* v,
+// part[tb][j] = sum_{i in row block tb, i >= j} M[i][j] v[i]; grid = lower (tb, cb) block pairs.  512 threads: four
+// row groups of 32 rows per column with eight independent accumulators each, so that a tile is four batches of
+// eight loads in flight per thread instead of a 32-deep dependent chain (37.5 -> 6.9 us for the 10 tiles of n = 500,
+// where this sweep is pure latency); the groups are combined in a fixed order.
+__global__ void __launch_bounds__(512) trmv_lower_t_part_kernel(const double* M, long long ld, const double* v,
                                                                 int np, double* part) {
     __shared__ double sv[128];
+    __shared__ double sp[3][128];
     int bid = blockIdx.x;
     int tb = (int)((sqrt(8.0 * (double)bid + 1.0) - 1.0) * 0.5);
     while ((long long)(tb + 1) * (tb + 2) / 2 <= bid) tb++;
     while ((long long)tb * (tb + 1) / 2 > bid) tb--;
     const int cb = bid - (int)((long long)tb * (tb + 1) / 2);
     const int tid = threadIdx.x;
-    sv[tid] = v[tb * 128 + tid];
+    const int c = tid & 127, rg = tid >> 7;
+    if (tid < 128) sv[tid] = v[tb * 128 + tid];
     __syncthreads();
-    const int j = cb * 128 + tid;
-    const double* Mp = M + (long long)tb * 128 * ld + j;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    const int j = cb * 128 + c;
+    const double* Mp = M + ((long long)tb * 128 + rg * 32) * ld + j;
+    const double* svp = sv + rg * 32;
+    double s[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) s[u] = 0.0;
     // on the diagonal block rows i < j hold zeros in M (strict upper part of L^-1), so no masking is needed
-#pragma unroll 4
-    for (int i = 0; i < 128; i += 4) {
-        s0 = fma(Mp[(long long)(i + 0) * ld], sv[i + 0], s0);
-        s1 = fma(Mp[(long long)(i + 1) * ld], sv[i + 1], s1);
-        s2 = fma(Mp[(long long)(i + 2) * ld], sv[i + 2], s2);
-        s3 = fma(Mp[(long long)(i + 3) * ld], sv[i + 3], s3);
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+        double m[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) m[u] = Mp[(long long)(i + u) * ld];
+#pragma unroll
+        for (int u = 0; u < 8; u++) s[u] = fma(m[u], svp[i + u], s[u]);
     }
-    part[(long long)tb * np + j] = (s0 + s1) + (s2 + s3);
+    const double tot = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+    if (rg > 0) sp[rg - 1][c] = tot;
+    __syncthreads();
+    if (rg == 0) part[(long long)tb * np + j] = (tot + sp[0][c]) + (sp[1][c] + sp[2][c]);
 }
 
 // alpha[j] = sum_{tb >= block(j)} part[tb][j]
