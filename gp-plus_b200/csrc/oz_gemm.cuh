@@ -1,0 +1,407 @@
+// FP64-equivalent tile GEMM on the INT8 tcgen05 tensor cores ("Ozaki" splitting), sm_100a.
+//
+// tcgen05 has no FP64 kind, and the exact DMMA path (dgemm_dmma.cuh) tops out at ~35 TFLOP/s.  The three O(N^3)
+// stages of the evaluation (trailing updates of the factorisation, the levels of the triangular inverse and
+// K^-1 = L^-T L^-1; reference: torch.linalg.cholesky + cholesky_backward reached through
+// MultivariateNormal.log_prob, optim/mll_scipy.py:37-39,123) can instead run as exact integer GEMMs:
+//
+//   every operand row r is scaled by a power of two, x = 2^e_r * sum_{p<7} d_p 256^-(p+1) (+ < 2^(e_r-56)),
+//   d_p signed base-256 digits ("digit planes", int8, written by oz_split.cuh), and
+//
+//   C[r,c] = beta C[r,c] + alpha 2^(ea_r + eb_c) sum_{lvl<7} 256^-(lvl+2) sum_{i+j=lvl} sum_k A_i[r,k] B_j[c,k]
+//
+//   (28 plane pairs; the dropped pairs i+j >= 7 are below 2^-54 of |row||col|).  Each of the 7 levels accumulates
+//   exactly in its own int32 TMEM accumulator: |d| <= 128, so K <= 16384 per accumulation cannot overflow.
+//
+// One CTA per SM, persistent over 128x64 output work items:
+//   warp 0 (one lane)  TMA producer: per 64-byte K chunk the 7 A planes (128 rows) and the 7 B planes (64 rows),
+//                      SWIZZLE_64B tiles, 2-stage mbarrier ring (84 KB per stage)
+//   warp 1 (one lane)  tcgen05.mma.cta_group::1.kind::i8, M=128 N=64 K=32, 56 MMAs per stage, accumulator of level lvl
+//                      at TMEM columns [64 lvl, 64 lvl + 64); tcgen05.commit frees the stage / publishes the tile
+//   warps 2-5          epilogue: tcgen05.ld (one TMEM lane = one output row per thread), Horner over the levels in
+//                      FP64, row/column power-of-two scales, alpha/beta read-modify-write of C
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dgemm_dmma.cuh"
+#include "tma.cuh"
+
+namespace gpp {
+
+constexpr int OZ_S = 7;            // digit planes per operand
+constexpr int OZ_BM = 128;         // output rows per work item (UMMA M)
+constexpr int OZ_BN = 64;          // output columns per work item (UMMA N): 7 accumulators x 64 columns = 448 of 512
+#ifndef GPP_OZ_BK
+#define GPP_OZ_BK 32
+#endif
+#ifndef GPP_OZ_STAGES
+#define GPP_OZ_STAGES 5
+#endif
+constexpr int OZ_BK = GPP_OZ_BK;   // K bytes (= int8 elements) per pipeline stage = swizzle width
+constexpr int OZ_STAGES = GPP_OZ_STAGES;
+constexpr int OZ_UMMA_K = 32;      // K of one kind::i8 MMA
+constexpr int OZ_A_TILE = OZ_BM * OZ_BK;                       // bytes per plane and stage
+constexpr int OZ_B_TILE = OZ_BN * OZ_BK;
+constexpr int OZ_STAGE_BYTES = OZ_S * (OZ_A_TILE + OZ_B_TILE); // 43008 (BK = 32) / 86016 (BK = 64)
+constexpr int OZ_SMEM_BYTES = OZ_STAGES * OZ_STAGE_BYTES + 1024 /*alignment slack*/ + 128 /*barriers*/;
+constexpr int OZ_THREADS = 192;
+constexpr int OZ_TMEM_COLS = 512;
+static_assert(OZ_SMEM_BYTES <= 232448, "oz_gemm shared memory exceeds the 227 KB per-CTA limit");
+static_assert(OZ_BK == 32 || OZ_BK == 64 || OZ_BK == 128, "K chunk must equal a swizzle width");
+
+// same K-range / tile-map vocabulary as GemmOp (dgemm_dmma.cuh); tiles are 128x128, a work item is half a tile
+struct OzGemmOp {
+    // digit planes: plane p of A is rows [p * a_plane_rows, (p+1) * a_plane_rows) of tensor map A (inner dim = k)
+    int a_plane_rows, b_plane_rows;
+    int a_row0, b_row0;              // plane row of tile row / tile column 0
+    int a_k0, b_k0;                  // plane k coordinate of K block 0
+    int a_zs_row, a_zs_k, b_zs_row, b_zs_k;   // batch steps in plane coordinates
+    const double* a_scale;           // 2^ea per plane row (same row coordinate as the planes, batch included)
+    const double* b_scale;
+    double* C;
+    int ldc;
+    long long c_zs;
+    int tiles_m, tiles_n, tiles_m_last;
+    int map, lower_filter, lower_off;
+    int klo_sel, klo_c, khi_sel, khi_c;
+    double alpha, beta;
+    int n_tiles;                     // 128x128 tiles per batch entry (set by launch_oz_gemm)
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, int8 x int8 -> int32
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier once every tcgen05 operation issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// 16 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile, rows of OZ_BK bytes, SWIZZLE_<OZ_BK>B: 8-row groups are 8 * OZ_BK bytes apart (SBO), LBO unused
+__device__ __forceinline__ uint64_t oz_smem_desc(uint32_t smem_addr) {
+    constexpr uint64_t layout = (OZ_BK == 128) ? 2 : (OZ_BK == 64 ? 4 : 6);
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)((8 * OZ_BK) >> 4) << 32) | (1ull << 46) | (layout << 61);
+}
+// kind::i8 instruction descriptor: D = s32, A = B = signed 8 bit, both K-major, M = 128, N = 64
+constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BN >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
+
+// work item -> (ti, tj, half); false: filtered out.  Lower-triangular map in super-rows of GS tile rows like the DMMA
+// kernel, so that the items in flight share a few row panels and a few column panels in L2.
+__device__ __forceinline__ bool oz_decode(const OzGemmOp& op, int item, int tm, int& ti, int& tj, int& half) {
+    constexpr int GS = 8;
+    half = item & 1;
+    const int tile_id = item >> 1;
+    if (op.map == MAP_TRI) {
+        const int bid = tile_id;
+        int gq = (int)((sqrt(8.0 * (double)bid + 1.0) - 1.0) * 0.5) / GS;
+        while ((long long)(gq + 1) * GS * ((gq + 1) * GS + 1) / 2 <= bid) gq++;
+        while ((long long)gq * GS * (gq * GS + 1) / 2 > bid) gq--;
+        const int r0g = gq * GS;
+        const int R = (op.tiles_m - r0g < GS) ? (op.tiles_m - r0g) : GS;
+        int local = bid - (int)((long long)r0g * (r0g + 1) / 2);
+        const int rect = r0g * R;
+        if (local < rect) {
+            tj = local / R;
+            ti = r0g + (local - tj * R);
+        } else {
+            local -= rect;
+            int c = 0;
+            while (local >= R - c) { local -= R - c; c++; }
+            tj = r0g + c;
+            ti = r0g + c + local;
+        }
+        return ti < tm;
+    }
+    const int r0g = (tile_id / (GS * op.tiles_n)) * GS;
+    const int R = (op.tiles_m - r0g < GS) ? (op.tiles_m - r0g) : GS;
+    const int local = tile_id - r0g * op.tiles_n;
+    tj = local / R;
+    ti = r0g + (local - tj * R);
+    if (ti >= tm) return false;
+    if (op.lower_filter && (ti + op.lower_off < tj)) return false;
+    return true;
+}
+__device__ __forceinline__ int oz_chunks(const OzGemmOp& op, int ti, int tj, int& klo) {
+    klo = op.klo_c + (op.klo_sel == KSEL_TI ? ti : (op.klo_sel == KSEL_TJ ? tj : 0));
+    const int khi = op.khi_c + (op.khi_sel == KSEL_TI ? ti : (op.khi_sel == KSEL_TJ ? tj : 0));
+    return (khi > klo) ? (khi - klo) * (TILE / OZ_BK) : 0;
+}
+
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const OzGemmOp op) {
+    extern __shared__ uint8_t oz_smem_raw[];
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(oz_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + OZ_STAGES * OZ_STAGE_BYTES);
+    uint64_t* full = bars;                          // [OZ_STAGES] TMA -> MMA
+    uint64_t* empty = bars + OZ_STAGES;             // [OZ_STAGES] MMA -> TMA
+    uint64_t* tmem_full = bars + 2 * OZ_STAGES;     // MMA -> epilogue
+    uint64_t* tmem_empty = bars + 2 * OZ_STAGES + 1;  // epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * OZ_STAGES + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int z = blockIdx.y;
+    const int tm = (z == (int)gridDim.y - 1) ? op.tiles_m_last : op.tiles_m;
+    const int n_items = op.n_tiles * 2;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < OZ_STAGES; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 4);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, OZ_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                int ti, tj, half, klo;
+                if (!oz_decode(op, item, tm, ti, tj, half)) continue;
+                const int nch = oz_chunks(op, ti, tj, klo);
+                const int a_row = op.a_row0 + z * op.a_zs_row + ti * TILE;
+                const int b_row = op.b_row0 + z * op.b_zs_row + tj * TILE + half * OZ_BN;
+                const int ka = op.a_k0 + z * op.a_zs_k + klo * TILE;
+                const int kb = op.b_k0 + z * op.b_zs_k + klo * TILE;
+                for (int c = 0; c < nch; c++) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full[stage], OZ_STAGE_BYTES);
+                    uint8_t* sa = base + stage * OZ_STAGE_BYTES;
+                    uint8_t* sb = sa + OZ_S * OZ_A_TILE;
+#pragma unroll
+                    for (int p = 0; p < OZ_S; p++) {
+                        // low planes first: the MMA warp consumes the levels in increasing order
+                        tma_load_2d(sa + p * OZ_A_TILE, &tmA, ka + c * OZ_BK, p * op.a_plane_rows + a_row, &full[stage]);
+                        tma_load_2d(sb + p * OZ_B_TILE, &tmB, kb + c * OZ_BK, p * op.b_plane_rows + b_row, &full[stage]);
+                    }
+                    if (++stage == OZ_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        uint32_t stage = 0, phase = 0, tphase = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            int ti, tj, half, klo;
+            if (!oz_decode(op, item, tm, ti, tj, half)) continue;
+            const int nch = oz_chunks(op, ti, tj, klo);
+            if (nch == 0) continue;
+            mbar_wait(tmem_empty, tphase ^ 1);   // the epilogue has drained the previous item's accumulators
+            tc_fence_after();
+            for (int c = 0; c < nch; c++) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = smem_u32(base + stage * OZ_STAGE_BYTES);
+                    const uint32_t sb = sa + OZ_S * OZ_A_TILE;
+#pragma unroll
+                    for (int ks = 0; ks < OZ_BK / OZ_UMMA_K; ks++) {
+#pragma unroll
+                        for (int lvl = 0; lvl < OZ_S; lvl++) {
+#pragma unroll
+                            for (int i = 0; i <= lvl; i++) {
+                                const int j = lvl - i;
+                                const uint64_t ad = oz_smem_desc(sa + i * OZ_A_TILE + ks * OZ_UMMA_K);
+                                const uint64_t bd = oz_smem_desc(sb + j * OZ_B_TILE + ks * OZ_UMMA_K);
+                                umma_i8(tmem_base + lvl * OZ_BN, ad, bd, OZ_IDESC, (c > 0 || ks > 0 || i > 0) ? 1u : 0u);
+                            }
+                        }
+                    }
+                    umma_commit(&empty[stage]);                 // stage reusable once these MMAs have read it
+                    if (c == nch - 1) umma_commit(tmem_full);   // accumulators complete
+                }
+                __syncwarp();
+                if (++stage == OZ_STAGES) { stage = 0; phase ^= 1; }
+            }
+            tphase ^= 1;
+        }
+    } else {
+        // ===== epilogue: TMEM lane quarter (warp % 4), one output row per thread =====
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        uint32_t tphase = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            int ti, tj, half, klo;
+            if (!oz_decode(op, item, tm, ti, tj, half)) continue;
+            const int nch = oz_chunks(op, ti, tj, klo);
+            double* Crow = op.C + (long long)z * op.c_zs + ((long long)ti * TILE + row) * op.ldc + (long long)tj * TILE +
+                           half * OZ_BN;
+            const double alpha = op.alpha, beta = op.beta;
+            if (nch == 0) {
+                // empty K range: C <- beta C
+#pragma unroll 4
+                for (int c = 0; c < OZ_BN; c += 2) {
+                    double2* p2 = reinterpret_cast<double2*>(Crow + c);
+                    double2 o = make_double2(0.0, 0.0);
+                    if (beta != 0.0) { o = *p2; o.x *= beta; o.y *= beta; }
+                    *p2 = o;
+                }
+                continue;
+            }
+            const double sa = alpha * op.a_scale[op.a_row0 + z * op.a_zs_row + ti * TILE + row] * (1.0 / 65536.0);
+            const double* sbp = op.b_scale + op.b_row0 + z * op.b_zs_row + tj * TILE + half * OZ_BN;
+            // C and the column scales of a 16-column group are fetched before the accumulators are read (for the
+            // first group: before the item's MMAs have finished), so that their latency is not paid per element
+            double2 old[8], sb2[8];
+            auto prefetch = [&](int cg) {
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    sb2[e] = *reinterpret_cast<const double2*>(sbp + cg * 16 + 2 * e);
+                    old[e] = (beta != 0.0) ? *reinterpret_cast<const double2*>(Crow + cg * 16 + 2 * e)
+                                           : make_double2(0.0, 0.0);
+                }
+            };
+            prefetch(0);
+            mbar_wait(tmem_full, tphase);
+            tc_fence_after();
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int cg = 0; cg < OZ_BN / 16; cg++) {
+                int v[OZ_S][16];
+#pragma unroll
+                for (int lvl = 0; lvl < OZ_S; lvl++) tmem_ld16(trow + lvl * OZ_BN + cg * 16, v[lvl]);
+                tmem_ld_wait();
+                double2 o[8];
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    double s0 = (double)v[OZ_S - 1][2 * e], s1 = (double)v[OZ_S - 1][2 * e + 1];
+#pragma unroll
+                    for (int lvl = OZ_S - 2; lvl >= 0; lvl--) {
+                        s0 = fma(s0, 1.0 / 256.0, (double)v[lvl][2 * e]);
+                        s1 = fma(s1, 1.0 / 256.0, (double)v[lvl][2 * e + 1]);
+                    }
+                    o[e].x = fma(beta, old[e].x, s0 * sa * sb2[e].x);
+                    o[e].y = fma(beta, old[e].y, s1 * sa * sb2[e].y);
+                }
+                double* dst = Crow + cg * 16;
+                if (cg + 1 < OZ_BN / 16) prefetch(cg + 1);
+#pragma unroll
+                for (int e = 0; e < 8; e++) *reinterpret_cast<double2*>(dst + 2 * e) = o[e];
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty);
+            tphase ^= 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, OZ_TMEM_COLS);
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------
+typedef CUresult (*oz_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline oz_encode_fn oz_encoder() {
+    static oz_encode_fn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess ||
+            qr != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<oz_encode_fn>(p);
+    }();
+    return fn;
+}
+
+// tensor map over stacked digit planes: inner dimension k (bytes), rows = OZ_S * plane_rows, row pitch `pitch` bytes
+inline cudaError_t oz_make_map(CUtensorMap* tm, const int8_t* planes, long long k_extent, long long rows_total,
+                               long long pitch, int box_rows) {
+    oz_encode_fn enc = oz_encoder();
+    if (!enc) return cudaErrorNotSupported;
+    cuuint64_t dims[2] = {(cuuint64_t)k_extent, (cuuint64_t)rows_total};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch};
+    cuuint32_t box[2] = {(cuuint32_t)OZ_BK, (cuuint32_t)box_rows};
+    cuuint32_t es[2] = {1, 1};
+    const CUtensorMapSwizzle sw = (OZ_BK == 128) ? CU_TENSOR_MAP_SWIZZLE_128B
+                                                 : (OZ_BK == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t*>(planes), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+inline cudaError_t oz_set_attributes() {
+    return cudaFuncSetAttribute(oz_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES);
+}
+
+inline int g_oz_ctas = GEMM_NUM_SMS;   // persistent grid (one CTA per SM)
+
+inline cudaError_t launch_oz_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const OzGemmOp& op_in, int nbatch,
+                                  cudaStream_t st) {
+    OzGemmOp op = op_in;
+    if (op.map == MAP_TRI) op.n_tiles = op.tiles_m * (op.tiles_m + 1) / 2;
+    else op.n_tiles = op.tiles_m * op.tiles_n;
+    if (op.n_tiles <= 0 || nbatch <= 0) return cudaSuccess;
+    int gx = op.n_tiles * 2;
+    const int cap = (g_oz_ctas + nbatch - 1) / nbatch;
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    count_launch();
+    oz_gemm_kernel<<<dim3(gx, nbatch), OZ_THREADS, OZ_SMEM_BYTES, st>>>(tmA, tmB, op);
+    return cudaGetLastError();
+}
+
+inline OzGemmOp oz_default() {
+    OzGemmOp op{};
+    op.alpha = 1.0;
+    op.beta = 0.0;
+    op.map = MAP_RECT;
+    op.klo_sel = KSEL_CONST;
+    op.khi_sel = KSEL_CONST;
+    op.tiles_n = 1;
+    return op;
+}
+
+}  // namespace gpp
