@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "dgemm_dmma.cuh"
+#include "oz_chol.cuh"
 
 namespace gpp {
 
@@ -454,6 +455,8 @@ inline cudaError_t chol_set_attributes() {
     cudaError_t e = cudaFuncSetAttribute(leaf_potrf_trinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          LEAF2_SMEM_BYTES);
     if (e != cudaSuccess) return e;
+    e = oz_set_attributes();
+    if (e != cudaSuccess) return e;
     return gemm_set_attributes();
 }
 
@@ -679,11 +682,12 @@ inline int g_lookahead_depth = 2;  // 1: the next panel waits for the whole prev
 inline int g_overlap_inverse = 1;   // start the early part of L^-1 (trtri_early) as soon as its columns of L are final
 
 // defined below; X is the scratch of the triangular inverse (may be null: no overlap)
-inline cudaError_t trtri_early(const double* L, double* M, double* X, int ld, int T, cudaStream_t st);
 inline int trtri_split_point(int T);
 
+inline cudaError_t trtri_early(const double* L, double* M, double* X, int ld, int T, cudaStream_t st, OzCtx* oz);
+
 inline cudaError_t potrf_lookahead(double* A, double* M, int ld, int T, double* logdet_part, int* info,
-                                   cudaStream_t st, CholLookahead& la, double* X = nullptr) {
+                                   cudaStream_t st, CholLookahead& la, double* X = nullptr, OzCtx* oz = nullptr) {
     // K of the trailing update: wide panels only pay off when the trailing matrix is large (measured:
     // N = 16384 59.0 -> 56.6 ms with 8, N = 8192 12.3 -> 12.8 ms; round 2, whole evaluation at N = 16384:
     // 139.3 ms with 8, 138.4 with 12, 138.6 with 16)
@@ -711,7 +715,7 @@ inline cudaError_t potrf_lookahead(double* A, double* M, int ld, int T, double* 
         if (overlap && !la.inv_pending && pend >= H) {
             // the first H tile columns of L are final: their share of L^-1 runs behind the rest of the factorisation
             GPP_TRY(cudaStreamWaitEvent(la.inv, la.ev_pf[p], 0));
-            GPP_TRY(trtri_early(A, M, X, ld, T, la.inv));
+            GPP_TRY(trtri_early(A, M, X, ld, T, la.inv, oz));
             GPP_TRY(cudaEventRecord(la.inv_done, la.inv));
             la.inv_pending = true;
         }
@@ -720,7 +724,16 @@ inline cudaError_t potrf_lookahead(double* A, double* M, int ld, int T, double* 
         GPP_TRY(trailing_update(A, ld, T, p0, pend, pend, nend, la.side));  // U(p,p+1)
         if (nend < T) {
             GPP_TRY(cudaStreamWaitEvent(st, la.ev_pf[p], 0));
-            if (deep) {
+            if (oz_use_trailing(oz, T, nend)) {
+                // the bulk of the trailing update on the INT8-sliced GEMM: digit planes of the panel rows nend..T once,
+                // then U(p,p+2) and U(p,p+3..) as integer GEMMs (the next panel's own columns, U(p,p+1), stay on DMMA
+                // on the side stream: they are on the critical chain and read the FP64 panel directly)
+                GPP_TRY(oz_split_panel(*oz, A, ld, T, p0, pend, nend, p, st));
+                const int n2end = (deep && nend + PB < T) ? nend + PB : T;
+                GPP_TRY(oz_trailing_update(*oz, A, ld, T, p0, pend, nend, n2end, p, st));
+                GPP_TRY(cudaEventRecord(la.ev_tu[p], st));
+                if (n2end < T) GPP_TRY(oz_trailing_update(*oz, A, ld, T, p0, pend, n2end, T, p, st));
+            } else if (deep) {
                 const int n2end = (nend + PB < T) ? nend + PB : T;
                 GPP_TRY(trailing_update(A, ld, T, p0, pend, nend, n2end, st));  // U(p,p+2)
                 GPP_TRY(cudaEventRecord(la.ev_tu[p], st));
@@ -741,7 +754,7 @@ inline cudaError_t potrf_lookahead(double* A, double* M, int ld, int T, double* 
 // One level of the recursive doubling on the groups [g_lo, g_hi) of 2*hb tiles each:
 //   X21 = L21 * M11 (part & 1), then M21 = -M22 * X21 (part & 2); groups are independent (batched launch).
 inline cudaError_t trtri_level(const double* L, double* M, double* X, int ld, int T, int hb, int g_lo, int g_hi,
-                               int part, cudaStream_t st, int max_ctas = 0) {
+                               int part, cudaStream_t st, int max_ctas = 0, OzCtx* oz = nullptr) {
     int nb = 0, last_s2 = 0;  // groups of the range with a non-empty second half
     for (int gidx = g_lo; gidx < g_hi; gidx++) {
         int s2 = T - (gidx * 2 * hb + hb);
@@ -751,6 +764,7 @@ inline cudaError_t trtri_level(const double* L, double* M, double* X, int ld, in
         last_s2 = s2;
     }
     if (nb == 0) return cudaSuccess;
+    if (oz_use_level(oz, hb)) return oz_trtri_level(*oz, L, M, X, ld, hb, g_lo, nb, last_s2, part, st);
     const long long zs = (long long)2 * hb * TILE * ld + (long long)2 * hb * TILE;  // next group, diagonal step
     const long long base = (long long)g_lo * zs;
     const long long off21 = base + (long long)hb * TILE * ld;                        // block (hb, 0) of the group
@@ -801,9 +815,10 @@ inline cudaError_t trtri_level(const double* L, double* M, double* X, int ld, in
     return cudaSuccess;
 }
 
-inline cudaError_t trtri_doubling(const double* L, double* M, double* X, int ld, int T, cudaStream_t st) {
+inline cudaError_t trtri_doubling(const double* L, double* M, double* X, int ld, int T, cudaStream_t st,
+                                  OzCtx* oz = nullptr) {
     for (int hb = 1; hb < T; hb *= 2)
-        GPP_TRY(trtri_level(L, M, X, ld, T, hb, 0, (T + 2 * hb - 1) / (2 * hb), 3, st));
+        GPP_TRY(trtri_level(L, M, X, ld, T, hb, 0, (T + 2 * hb - 1) / (2 * hb), 3, st, 0, oz));
     return cudaSuccess;
 }
 
@@ -818,25 +833,27 @@ inline int trtri_split_point(int T) {
     while (H * 2 < T) H *= 2;
     return (T >= 2) ? H : 0;
 }
-inline cudaError_t trtri_early(const double* L, double* M, double* X, int ld, int T, cudaStream_t st) {
+inline cudaError_t trtri_early(const double* L, double* M, double* X, int ld, int T, cudaStream_t st, OzCtx* oz = nullptr) {
     const int H = trtri_split_point(T);
     if (H == 0) return cudaSuccess;
     for (int hb = 1; hb < H; hb *= 2)
-        GPP_TRY(trtri_level(L, M, X, ld, T, hb, 0, H / (2 * hb), 3, st));
-    return trtri_level(L, M, X, ld, T, H, 0, 1, 1, st);
+        GPP_TRY(trtri_level(L, M, X, ld, T, hb, 0, H / (2 * hb), 3, st, 0, oz));
+    return trtri_level(L, M, X, ld, T, H, 0, 1, 1, st, 0, oz);
 }
-inline cudaError_t trtri_late(const double* L, double* M, double* X, int ld, int T, cudaStream_t st) {
+inline cudaError_t trtri_late(const double* L, double* M, double* X, int ld, int T, cudaStream_t st, OzCtx* oz = nullptr) {
     const int H = trtri_split_point(T);
     if (H == 0) return cudaSuccess;
     for (int hb = 1; hb < H; hb *= 2)
-        GPP_TRY(trtri_level(L, M, X, ld, T, hb, H / (2 * hb), (T + 2 * hb - 1) / (2 * hb), 3, st));
-    return trtri_level(L, M, X, ld, T, H, 0, 1, 2, st);
+        GPP_TRY(trtri_level(L, M, X, ld, T, hb, H / (2 * hb), (T + 2 * hb - 1) / (2 * hb), 3, st, 0, oz));
+    return trtri_level(L, M, X, ld, T, H, 0, 1, 2, st, 0, oz);
 }
 
 // Kinv = M^T M over the lower tiles; M lower: k-blocks [ti, T).  The hot path reads lower tiles only (the gradient
 // pass and the noise-gradient diagonal), so the upper triangle is not written unless `mirror` is set: the mirrored
 // store was 3.6x the algorithmic DRAM traffic of this launch (strided 8-byte stores, profiles/dgemm_traffic.json).
-inline cudaError_t lauum_full(const double* M, double* Kinv, int ld, int T, cudaStream_t st, int mirror = 0) {
+inline cudaError_t lauum_full(const double* M, double* Kinv, int ld, int T, cudaStream_t st, int mirror = 0,
+                              OzCtx* oz = nullptr) {
+    if (!mirror && oz_use_lauum(oz, T)) return oz_lauum(*oz, M, Kinv, ld, T, st);
     GemmOp op = gemm_default();
     op.A = M;
     op.lda = ld;

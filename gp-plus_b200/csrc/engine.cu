@@ -93,6 +93,7 @@ struct gpp_handle {
     gpp_timings tm;
     CholLookahead la;
     bool use_lookahead = true;
+    OzCtx* oz = nullptr;     // INT8-sliced tcgen05 path of the O(N^3) stages (large problems; GPP_FP64=dmma turns it off)
     // CUDA-graph replay of one whole evaluation (small problems are launch-bound): [want_grad]
     cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
     long long graph_kernels[2] = {0, 0};
@@ -155,6 +156,10 @@ static void destroy_now(gpp_handle* h) {
     for (int i = 0; i < 2; i++)
         if (h->graph_exec[i]) cudaGraphExecDestroy(h->graph_exec[i]);
     h->la.destroy();
+    if (h->oz) {
+        h->oz->destroy();
+        delete h->oz;
+    }
     if (h->st) cudaStreamDestroy(h->st);
     delete h;
 }
@@ -380,6 +385,20 @@ extern "C" int gpp_create(const gpp_problem* p, int device, gpp_handle** out) {
         if ((e = getenv("GPP_EARLY_OUT")) != nullptr) h->early_out = atoi(e) != 0;
     }
     CKH(h->la.init(h->T));
+    {
+        // FP64 work of the O(N^3) stages: exact integer GEMMs on the INT8 tcgen05 tensor cores from Np = 4096 up
+        // (below that the stages are latency-bound and the DMMA kernels win); GPP_FP64=dmma keeps everything on DMMA
+        const char* e = getenv("GPP_FP64");
+        bool int8 = h->T >= 32;
+        if (e) int8 = int8 && strcmp(e, "dmma") != 0;
+        if (int8) {
+            h->oz = new OzCtx();
+            if ((e = getenv("GPP_OZ_MIN_TRAIL")) != nullptr) h->oz->min_trailing_tiles = atoi(e);
+            if ((e = getenv("GPP_OZ_MIN_LEVEL")) != nullptr) h->oz->min_level_tiles = atoi(e);
+            if ((e = getenv("GPP_OZ_IPC")) != nullptr) g_oz_items_per_cta = atoi(e) > 0 ? atoi(e) : 2;
+            CKH(h->oz->init((int)h->np));
+        }
+    }
 
     h->hyp_len = h->dq + h->n_pass * h->n_combo * h->dz + h->n_noise + h->n_mean + 2;
     h->res_len = 4 + h->dq + h->n_noise + h->n_mean;
@@ -562,7 +581,7 @@ static int stage_factor(gpp_handle* h) {
     }
     mark(h, EV_COV);
     if (h->use_lookahead)
-        CK(potrf_lookahead(h->A, h->M, (int)h->np, h->T, h->logdet_part, h->info, h->st, h->la, h->S));
+        CK(potrf_lookahead(h->A, h->M, (int)h->np, h->T, h->logdet_part, h->info, h->st, h->la, h->S, h->oz));
     else
         CK(potrf_blocked(h->A, h->M, (int)h->np, h->T, h->logdet_part, h->info, h->st));
     mark(h, EV_CHOL);
@@ -575,9 +594,9 @@ static int stage_inverse_solve(gpp_handle* h) {
         // the leading part of L^-1 was started behind the factorisation (trtri_early): join it, finish the rest
         CK(cudaStreamWaitEvent(h->st, h->la.inv_done, 0));
         h->la.inv_pending = false;
-        CK(trtri_late(h->A, h->M, h->S, (int)h->np, h->T, h->st));
+        CK(trtri_late(h->A, h->M, h->S, (int)h->np, h->T, h->st, h->oz));
     } else {
-        CK(trtri_doubling(h->A, h->M, h->S, (int)h->np, h->T, h->st));
+        CK(trtri_doubling(h->A, h->M, h->S, (int)h->np, h->T, h->st, h->oz));
     }
     mark(h, EV_TRTRI);
     trmv_lower_kernel<<<(int)(h->np / 8), 256, 0, h->st>>>(h->M, h->np, h->r, (int)h->np, h->v);
@@ -594,7 +613,7 @@ static int stage_inverse_solve(gpp_handle* h) {
 }
 
 static int stage_grad(gpp_handle* h) {
-    CK(lauum_full(h->M, h->S, (int)h->np, h->T, h->st));
+    CK(lauum_full(h->M, h->S, (int)h->np, h->T, h->st, 0, h->oz));
     mark(h, EV_LAUUM);
     GradArgs ga;
     memset(&ga, 0, sizeof(ga));

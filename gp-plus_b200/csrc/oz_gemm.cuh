@@ -13,9 +13,10 @@
 //   (28 plane pairs; the dropped pairs i+j >= 7 are below 2^-54 of |row||col|).  Each of the 7 levels accumulates
 //   exactly in its own int32 TMEM accumulator: |d| <= 128, so K <= 16384 per accumulation cannot overflow.
 //
-// One CTA per SM, persistent over 128x64 output work items:
+// One CTA per SM (172 KB of shared memory, all of TMEM), each looping over a few 128x64 output work items:
 //   warp 0 (one lane)  TMA producer: per 64-byte K chunk the 7 A planes (128 rows) and the 7 B planes (64 rows),
-//                      SWIZZLE_64B tiles, 2-stage mbarrier ring (84 KB per stage)
+//                      SWIZZLE_64B tiles, 2-stage mbarrier ring (84 KB per stage; 32-byte chunks x 5 stages measured
+//                      5-8 % slower)
 //   warp 1 (one lane)  tcgen05.mma.cta_group::1.kind::i8, M=128 N=64 K=32, 56 MMAs per stage, accumulator of level lvl
 //                      at TMEM columns [64 lvl, 64 lvl + 64); tcgen05.commit frees the stage / publishes the tile
 //   warps 2-5          epilogue: tcgen05.ld (one TMEM lane = one output row per thread), Horner over the levels in
@@ -34,10 +35,10 @@ constexpr int OZ_S = 7;            // digit planes per operand
 constexpr int OZ_BM = 128;         // output rows per work item (UMMA M)
 constexpr int OZ_BN = 64;          // output columns per work item (UMMA N): 7 accumulators x 64 columns = 448 of 512
 #ifndef GPP_OZ_BK
-#define GPP_OZ_BK 32
+#define GPP_OZ_BK 64
 #endif
 #ifndef GPP_OZ_STAGES
-#define GPP_OZ_STAGES 5
+#define GPP_OZ_STAGES 2
 #endif
 constexpr int OZ_BK = GPP_OZ_BK;   // K bytes (= int8 elements) per pipeline stage = swizzle width
 constexpr int OZ_STAGES = GPP_OZ_STAGES;
@@ -376,17 +377,19 @@ inline cudaError_t oz_set_attributes() {
     return cudaFuncSetAttribute(oz_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES);
 }
 
-inline int g_oz_ctas = GEMM_NUM_SMS;   // persistent grid (one CTA per SM)
+// items_per_cta: CTAs are NOT persistent over the whole launch -- each handles about this many 128x64 items
+// (grid-stride), so that SMs are handed back every few items and higher-priority streams (the panel chain of the
+// factorisation) get in; the hardware block scheduler does the load balancing.
+inline int g_oz_items_per_cta = 2;
 
 inline cudaError_t launch_oz_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const OzGemmOp& op_in, int nbatch,
-                                  cudaStream_t st) {
+                                  cudaStream_t st, int items_per_cta = 0) {
     OzGemmOp op = op_in;
     if (op.map == MAP_TRI) op.n_tiles = op.tiles_m * (op.tiles_m + 1) / 2;
     else op.n_tiles = op.tiles_m * op.tiles_n;
     if (op.n_tiles <= 0 || nbatch <= 0) return cudaSuccess;
-    int gx = op.n_tiles * 2;
-    const int cap = (g_oz_ctas + nbatch - 1) / nbatch;
-    if (gx > cap) gx = cap;
+    const int ipc = items_per_cta > 0 ? items_per_cta : g_oz_items_per_cta;
+    int gx = (op.n_tiles * 2 + ipc - 1) / ipc;
     if (gx < 1) gx = 1;
     count_launch();
     oz_gemm_kernel<<<dim3(gx, nbatch), OZ_THREADS, OZ_SMEM_BYTES, st>>>(tmA, tmB, op);

@@ -43,12 +43,14 @@ __device__ __forceinline__ void oz_digits(double x, double inv56, int8_t (&d)[OZ
 // batched: blockIdx.y = batch entry; element (r,k) of entry z at X[z*x_zs + r*ld + k], plane element at
 // planes[p*plane_stride + z*pl_zs + r*pitch + k], scale[z*sc_zs + r].
 __global__ void __launch_bounds__(256) oz_split_rows_kernel(const double* __restrict__ X, long long ld, long long x_zs,
-                                                            int rows, int rows_last, int kcols, int8_t* __restrict__ planes,
+                                                            int rows, int rows_last, int kcols_all, int kcols_last,
+                                                            int8_t* __restrict__ planes,
                                                             long long pitch, long long plane_stride, long long pl_zs,
                                                             double* __restrict__ scale, long long sc_zs) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int z = blockIdx.y;
     const int nrows = (z == (int)gridDim.y - 1) ? rows_last : rows;
+    const int kcols = (z == (int)gridDim.y - 1) ? kcols_last : kcols_all;
     const int r = blockIdx.x * 8 + warp;
     if (r >= nrows) return;
     const double* x = X + (long long)z * x_zs + (long long)r * ld;
@@ -181,11 +183,12 @@ struct OzPlanes {
 // rows x kcols block of a k-contiguous operand; destination plane coordinates (row_dst, k_dst)
 inline cudaError_t oz_split_rows(const double* X, long long ld, long long x_zs, int rows, int rows_last, int kcols,
                                  const OzPlanes& P, long long row_dst, long long k_dst, long long dst_zs_row,
-                                 long long dst_zs_k, int nbatch, cudaStream_t st) {
+                                 long long dst_zs_k, int nbatch, cudaStream_t st, int kcols_last = -1) {
     if (rows <= 0 || kcols <= 0 || nbatch <= 0) return cudaSuccess;
     count_launch();
     dim3 grid((rows + 7) / 8, nbatch);
-    oz_split_rows_kernel<<<grid, 256, 0, st>>>(X, ld, x_zs, rows, rows_last, kcols, P.planes + row_dst * P.pitch + k_dst,
+    oz_split_rows_kernel<<<grid, 256, 0, st>>>(X, ld, x_zs, rows, rows_last, kcols, kcols_last < 0 ? kcols : kcols_last,
+                                               P.planes + row_dst * P.pitch + k_dst,
                                                P.pitch, P.plane_stride(), dst_zs_row * P.pitch + dst_zs_k, P.scale + row_dst,
                                                dst_zs_row);
     return cudaGetLastError();
