@@ -666,15 +666,21 @@ inline cudaError_t trailing_update(double* A, int ld, int T, int p0, int pend, i
 // panels wider than PANEL_BLOCKS are factored recursively: left half, update of the right half with the left
 // (one DMMA GEMM at K = width/2), right half -- so that only PANEL_BLOCKS-wide pieces run at K = 128
 inline cudaError_t panel_factor(double* A, double* M, int ld, int T, int p0, int pend, double* logdet_part, int* info,
-                                cudaStream_t st) {
+                                cudaStream_t st, OzCtx* oz = nullptr) {
     const int w = pend - p0;
     if (w <= PANEL_BASE) return panel_factor_base(A, M, ld, T, p0, pend, logdet_part, info, st);
     int half = PANEL_BASE;
     while (half * 2 < w) half *= 2;
     const int mid = p0 + half;
-    GPP_TRY(panel_factor(A, M, ld, T, p0, mid, logdet_part, info, st));
-    GPP_TRY(trailing_update(A, ld, T, p0, mid, mid, pend, st));
-    return panel_factor(A, M, ld, T, mid, pend, logdet_part, info, st);
+    GPP_TRY(panel_factor(A, M, ld, T, p0, mid, logdet_part, info, st, oz));
+    if (oz && oz->ready && oz->inner_min_k > 0 && half >= oz->inner_min_k && oz_use_trailing(oz, T, mid)) {
+        // wide in-panel update on the INT8-sliced GEMM (planes of the left half, rows mid..T; scale slot 4)
+        GPP_TRY(oz_split_panel(*oz, A, ld, T, p0, mid, mid, 4, st));
+        GPP_TRY(oz_trailing_update(*oz, A, ld, T, p0, mid, mid, pend, 4, st));
+    } else {
+        GPP_TRY(trailing_update(A, ld, T, p0, mid, mid, pend, st));
+    }
+    return panel_factor(A, M, ld, T, mid, pend, logdet_part, info, st, oz);
 }
 
 inline int g_lookahead_depth = 2;  // 1: the next panel waits for the whole previous trailing update; 2: see below
@@ -709,7 +715,11 @@ inline cudaError_t potrf_lookahead(double* A, double* M, int ld, int T, double* 
     for (int p = 0; p < NP; p++) {
         const int p0 = p * PB;
         const int pend = (p0 + PB < T) ? p0 + PB : T;
-        GPP_TRY(panel_factor(A, M, ld, T, p0, pend, logdet_part, info, la.side));
+        GPP_TRY(panel_factor(A, M, ld, T, p0, pend, logdet_part, info, la.side, oz));
+        // with U(p,p+1) on the INT8-sliced GEMM the digit planes of the whole panel (rows pend..T) are cut here, on the
+        // side stream, and the main stream's updates reuse them
+        const bool ozp = oz && oz->next_on_oz && oz_use_trailing(oz, T, pend);
+        if (ozp) GPP_TRY(oz_split_panel(*oz, A, ld, T, p0, pend, pend, p & 3, la.side));
         GPP_TRY(cudaEventRecord(la.ev_pf[p], la.side));
         if (pend >= T) break;
         if (overlap && !la.inv_pending && pend >= H) {
@@ -721,18 +731,18 @@ inline cudaError_t potrf_lookahead(double* A, double* M, int ld, int T, double* 
         }
         const int nend = (pend + PB < T) ? pend + PB : T;
         if (last_ev >= 0) GPP_TRY(cudaStreamWaitEvent(la.side, la.ev_tu[last_ev], 0));
-        GPP_TRY(trailing_update(A, ld, T, p0, pend, pend, nend, la.side));  // U(p,p+1)
+        if (ozp) GPP_TRY(oz_trailing_update(*oz, A, ld, T, p0, pend, pend, nend, p & 3, la.side));  // U(p,p+1)
+        else GPP_TRY(trailing_update(A, ld, T, p0, pend, pend, nend, la.side));
         if (nend < T) {
             GPP_TRY(cudaStreamWaitEvent(st, la.ev_pf[p], 0));
             if (oz_use_trailing(oz, T, nend)) {
                 // the bulk of the trailing update on the INT8-sliced GEMM: digit planes of the panel rows nend..T once,
-                // then U(p,p+2) and U(p,p+3..) as integer GEMMs (the next panel's own columns, U(p,p+1), stay on DMMA
-                // on the side stream: they are on the critical chain and read the FP64 panel directly)
-                GPP_TRY(oz_split_panel(*oz, A, ld, T, p0, pend, nend, p, st));
+                // then U(p,p+2) and U(p,p+3..) as integer GEMMs
+                if (!ozp) GPP_TRY(oz_split_panel(*oz, A, ld, T, p0, pend, nend, p & 3, st));
                 const int n2end = (deep && nend + PB < T) ? nend + PB : T;
-                GPP_TRY(oz_trailing_update(*oz, A, ld, T, p0, pend, nend, n2end, p, st));
+                GPP_TRY(oz_trailing_update(*oz, A, ld, T, p0, pend, nend, n2end, p & 3, st));
                 GPP_TRY(cudaEventRecord(la.ev_tu[p], st));
-                if (n2end < T) GPP_TRY(oz_trailing_update(*oz, A, ld, T, p0, pend, n2end, T, p, st));
+                if (n2end < T) GPP_TRY(oz_trailing_update(*oz, A, ld, T, p0, pend, n2end, T, p & 3, st));
             } else if (deep) {
                 const int n2end = (nend + PB < T) ? nend + PB : T;
                 GPP_TRY(trailing_update(A, ld, T, p0, pend, nend, n2end, st));  // U(p,p+2)

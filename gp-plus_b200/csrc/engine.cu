@@ -396,6 +396,8 @@ extern "C" int gpp_create(const gpp_problem* p, int device, gpp_handle** out) {
             if ((e = getenv("GPP_OZ_MIN_TRAIL")) != nullptr) h->oz->min_trailing_tiles = atoi(e);
             if ((e = getenv("GPP_OZ_MIN_LEVEL")) != nullptr) h->oz->min_level_tiles = atoi(e);
             if ((e = getenv("GPP_OZ_IPC")) != nullptr) g_oz_items_per_cta = atoi(e) > 0 ? atoi(e) : 2;
+            if ((e = getenv("GPP_OZ_NEXT")) != nullptr) h->oz->next_on_oz = atoi(e);
+            if ((e = getenv("GPP_OZ_INNER")) != nullptr) h->oz->inner_min_k = atoi(e);
             CKH(h->oz->init((int)h->np));
         }
     }

@@ -18,7 +18,9 @@ struct OzCtx {
     bool ready = false;
     int np = 0, T = 0;
     OzPlanes PP, PA, PB;
-    double* pscale[4] = {nullptr, nullptr, nullptr, nullptr};
+    double* pscale[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // [4]: in-panel updates (side stream only)
+    int next_on_oz = 1;            // U(p,p+1), the update of the next panel's own columns, also runs here
+    int inner_min_k = 4;           // in-panel (recursive) updates with K >= this many tiles run here; 0 = never
     CUtensorMap mPP_a, mPP_b, mPA_a, mPB_a, mPB_b;
     int min_trailing_tiles = 12;   // smaller trailing matrices stay on DMMA (too few 128x64 items for 148 SMs)
     int min_level_tiles = 4;       // inverse levels below this half-width stay on DMMA (K < 512)
@@ -53,7 +55,7 @@ struct OzCtx {
         if ((e = alloc_planes(PP, np, bytes)) != cudaSuccess) return e;
         if ((e = alloc_planes(PA, np, bytes)) != cudaSuccess) return e;
         if ((e = alloc_planes(PB, np, bytes)) != cudaSuccess) return e;
-        for (int i = 0; i < 4; i++)
+        for (int i = 0; i < 5; i++)
             if ((e = cudaMalloc(&pscale[i], sizeof(double) * np)) != cudaSuccess) return e;
         const long long rows = (long long)OZ_S * np;
         if ((e = oz_make_map(&mPP_a, PP.planes, np, rows, np, OZ_BM)) != cudaSuccess) return e;
@@ -68,7 +70,7 @@ struct OzCtx {
         free_planes(PP);
         free_planes(PA);
         free_planes(PB);
-        for (int i = 0; i < 4; i++) {
+        for (int i = 0; i < 5; i++) {
             if (pscale[i]) cudaFree(pscale[i]);
             pscale[i] = nullptr;
         }
@@ -78,11 +80,11 @@ struct OzCtx {
 
 // digit planes of the factored panel p (tile columns [p0, pend), tile rows r0..T) -- the operand of every
 // trailing update with that panel on the main stream
-inline cudaError_t oz_split_panel(OzCtx& oz, const double* A, int ld, int T, int p0, int pend, int r0, int panel,
+inline cudaError_t oz_split_panel(OzCtx& oz, const double* A, int ld, int T, int p0, int pend, int r0, int slot,
                                   cudaStream_t st) {
     if (r0 >= T) return cudaSuccess;
     OzPlanes pp = oz.PP;
-    pp.scale = oz.pscale[panel & 3] - 0;   // indexed by absolute plane row like PP.scale
+    pp.scale = oz.pscale[slot];   // indexed by absolute plane row like PP.scale
     const int rows = (T - r0) * TILE;
     return oz_split_rows(A + (long long)r0 * TILE * ld + (long long)p0 * TILE, ld, 0, rows, rows, (pend - p0) * TILE, pp,
                          (long long)r0 * TILE, (long long)p0 * TILE, 0, 0, 1, st);
@@ -91,14 +93,14 @@ inline cudaError_t oz_split_panel(OzCtx& oz, const double* A, int ld, int T, int
 inline bool oz_use_trailing(const OzCtx* oz, int T, int c0) { return oz && oz->ready && (T - c0) >= oz->min_trailing_tiles; }
 
 // C[i,j] -= sum_{k in [p0,pend)} L[i,k] L[j,k] for tile rows i >= c0, tile columns j in [c0, c1), i >= j
-inline cudaError_t oz_trailing_update(OzCtx& oz, double* A, int ld, int T, int p0, int pend, int c0, int c1, int panel,
+inline cudaError_t oz_trailing_update(OzCtx& oz, double* A, int ld, int T, int p0, int pend, int c0, int c1, int slot,
                                       cudaStream_t st) {
     if (c1 <= c0 || c0 >= T) return cudaSuccess;
     OzGemmOp op = oz_default();
     op.a_plane_rows = op.b_plane_rows = oz.np;
     op.a_row0 = op.b_row0 = c0 * TILE;
     op.a_k0 = op.b_k0 = p0 * TILE;
-    op.a_scale = op.b_scale = oz.pscale[panel & 3];
+    op.a_scale = op.b_scale = oz.pscale[slot];
     op.C = A + (long long)c0 * TILE * ld + (long long)c0 * TILE;
     op.ldc = ld;
     op.tiles_m = op.tiles_m_last = T - c0;

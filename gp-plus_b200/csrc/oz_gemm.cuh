@@ -10,17 +10,23 @@
 //
 //   C[r,c] = beta C[r,c] + alpha 2^(ea_r + eb_c) sum_{lvl<7} 256^-(lvl+2) sum_{i+j=lvl} sum_k A_i[r,k] B_j[c,k]
 //
-//   (28 plane pairs; the dropped pairs i+j >= 7 are below 2^-54 of |row||col|).  Each of the 7 levels accumulates
-//   exactly in its own int32 TMEM accumulator: |d| <= 128, so K <= 16384 per accumulation cannot overflow.
+//   (28 plane pairs; the dropped pairs i+j >= 7 are below 2^-54 of |row||col|).  Every level accumulates exactly in
+//   its own int32 TMEM accumulator: |d| <= 128, so K <= 16384 per accumulation cannot overflow.
 //
-// One CTA per SM (172 KB of shared memory, all of TMEM), each looping over a few 128x64 output work items:
-//   warp 0 (one lane)  TMA producer: per 64-byte K chunk the 7 A planes (128 rows) and the 7 B planes (64 rows),
-//                      SWIZZLE_64B tiles, 2-stage mbarrier ring (84 KB per stage; 32-byte chunks x 5 stages measured
-//                      5-8 % slower)
-//   warp 1 (one lane)  tcgen05.mma.cta_group::1.kind::i8, M=128 N=64 K=32, 56 MMAs per stage, accumulator of level lvl
-//                      at TMEM columns [64 lvl, 64 lvl + 64); tcgen05.commit frees the stage / publishes the tile
-//   warps 2-5          epilogue: tcgen05.ld (one TMEM lane = one output row per thread), Horner over the levels in
-//                      FP64, row/column power-of-two scales, alpha/beta read-modify-write of C
+// Measured issue rates of tcgen05.mma.kind::i8 at M = 128 (tools/oz_lab rate): N = 64: 48 cycles (shared-memory
+// operand reads, 6 KB per MMA at 128 B/clk), N = 128: 64 cycles, N = 256: 128 cycles (both = 4.5 POPS).  N = 128 is
+// the narrowest shape that reaches the peak, and TMEM holds four 128-column accumulators, so a 128x128 output tile
+// is produced in two passes over K:
+//   pass 0: levels 0..3 (10 plane pairs, planes 0..3 of both operands),  C  = beta C + alpha * (...)
+//   pass 1: levels 4..6 (18 plane pairs, planes 0..6),                   C += alpha * (...)
+//
+// One CTA per SM (all of TMEM, 225 KB of shared memory), each looping over a few output tiles:
+//   warp 0 (one lane)  TMA producer: per 64-byte K chunk the planes the pass needs (128 rows x 64 B, SWIZZLE_64B),
+//                      2-slot mbarrier ring
+//   warp 1 (one lane)  tcgen05.mma.cta_group::1.kind::i8, M = N = 128, K = 32; tcgen05.commit frees the slot /
+//                      publishes the accumulators
+//   warps 2-9          epilogue: tcgen05.ld (TMEM lane = output row; two warps per lane quarter, 64 columns each),
+//                      Horner over the levels in FP64, power-of-two row / column scales, read-modify-write of C
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -32,27 +38,24 @@
 namespace gpp {
 
 constexpr int OZ_S = 7;            // digit planes per operand
+constexpr int OZ_L0 = 4;           // levels of pass 0 (accumulators 0..3); pass 1: levels 4..6 (accumulators 0..2)
 constexpr int OZ_BM = 128;         // output rows per work item (UMMA M)
-constexpr int OZ_BN = 64;          // output columns per work item (UMMA N): 7 accumulators x 64 columns = 448 of 512
-#ifndef GPP_OZ_BK
-#define GPP_OZ_BK 64
-#endif
-#ifndef GPP_OZ_STAGES
-#define GPP_OZ_STAGES 2
-#endif
-constexpr int OZ_BK = GPP_OZ_BK;   // K bytes (= int8 elements) per pipeline stage = swizzle width
-constexpr int OZ_STAGES = GPP_OZ_STAGES;
+constexpr int OZ_BN = 128;         // output columns per work item (UMMA N)
+constexpr int OZ_BK = 64;          // K bytes (= int8 elements) per ring slot = swizzle width
+constexpr int OZ_STAGES = 2;
 constexpr int OZ_UMMA_K = 32;      // K of one kind::i8 MMA
-constexpr int OZ_A_TILE = OZ_BM * OZ_BK;                       // bytes per plane and stage
+constexpr int OZ_A_TILE = OZ_BM * OZ_BK;                       // 8192 B per plane and slot
 constexpr int OZ_B_TILE = OZ_BN * OZ_BK;
-constexpr int OZ_STAGE_BYTES = OZ_S * (OZ_A_TILE + OZ_B_TILE); // 43008 (BK = 32) / 86016 (BK = 64)
+constexpr int OZ_STAGE_BYTES = OZ_S * (OZ_A_TILE + OZ_B_TILE); // 114688 (pass 1; pass 0 fills 65536 of it)
 constexpr int OZ_SMEM_BYTES = OZ_STAGES * OZ_STAGE_BYTES + 1024 /*alignment slack*/ + 128 /*barriers*/;
-constexpr int OZ_THREADS = 192;
+constexpr int OZ_EPI_WARPS = 8;
+constexpr int OZ_THREADS = 32 * (2 + OZ_EPI_WARPS);
 constexpr int OZ_TMEM_COLS = 512;
 static_assert(OZ_SMEM_BYTES <= 232448, "oz_gemm shared memory exceeds the 227 KB per-CTA limit");
 static_assert(OZ_BK == 32 || OZ_BK == 64 || OZ_BK == 128, "K chunk must equal a swizzle width");
+static_assert(OZ_L0 * OZ_BN <= OZ_TMEM_COLS && (OZ_S - OZ_L0) <= OZ_L0, "accumulators must fit in TMEM");
 
-// same K-range / tile-map vocabulary as GemmOp (dgemm_dmma.cuh); tiles are 128x128, a work item is half a tile
+// same K-range / tile-map vocabulary as GemmOp (dgemm_dmma.cuh); a work item is one 128x128 tile
 struct OzGemmOp {
     // digit planes: plane p of A is rows [p * a_plane_rows, (p+1) * a_plane_rows) of tensor map A (inner dim = k)
     int a_plane_rows, b_plane_rows;
@@ -128,12 +131,10 @@ __device__ __forceinline__ uint64_t oz_smem_desc(uint32_t smem_addr) {
 // kind::i8 instruction descriptor: D = s32, A = B = signed 8 bit, both K-major, M = 128, N = 64
 constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BN >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
 
-// work item -> (ti, tj, half); false: filtered out.  Lower-triangular map in super-rows of GS tile rows like the DMMA
+// work item -> (ti, tj); false: filtered out.  Lower-triangular map in super-rows of GS tile rows like the DMMA
 // kernel, so that the items in flight share a few row panels and a few column panels in L2.
-__device__ __forceinline__ bool oz_decode(const OzGemmOp& op, int item, int tm, int& ti, int& tj, int& half) {
+__device__ __forceinline__ bool oz_decode(const OzGemmOp& op, int tile_id, int tm, int& ti, int& tj) {
     constexpr int GS = 8;
-    half = item & 1;
-    const int tile_id = item >> 1;
     if (op.map == MAP_TRI) {
         const int bid = tile_id;
         int gq = (int)((sqrt(8.0 * (double)bid + 1.0) - 1.0) * 0.5) / GS;
@@ -184,7 +185,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int z = blockIdx.y;
     const int tm = (z == (int)gridDim.y - 1) ? op.tiles_m_last : op.tiles_m;
-    const int n_items = op.n_tiles * 2;
+    const int n_items = op.n_tiles;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -194,7 +195,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(&empty[s], 1);
         }
         mbar_init(tmem_full, 1);
-        mbar_init(tmem_empty, 4);
+        mbar_init(tmem_empty, OZ_EPI_WARPS);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, OZ_TMEM_COLS);
@@ -208,25 +209,26 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                int ti, tj, half, klo;
-                if (!oz_decode(op, item, tm, ti, tj, half)) continue;
+                int ti, tj, klo;
+                if (!oz_decode(op, item, tm, ti, tj)) continue;
                 const int nch = oz_chunks(op, ti, tj, klo);
                 const int a_row = op.a_row0 + z * op.a_zs_row + ti * TILE;
-                const int b_row = op.b_row0 + z * op.b_zs_row + tj * TILE + half * OZ_BN;
+                const int b_row = op.b_row0 + z * op.b_zs_row + tj * TILE;
                 const int ka = op.a_k0 + z * op.a_zs_k + klo * TILE;
                 const int kb = op.b_k0 + z * op.b_zs_k + klo * TILE;
-                for (int c = 0; c < nch; c++) {
-                    mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full[stage], OZ_STAGE_BYTES);
-                    uint8_t* sa = base + stage * OZ_STAGE_BYTES;
-                    uint8_t* sb = sa + OZ_S * OZ_A_TILE;
-#pragma unroll
-                    for (int p = 0; p < OZ_S; p++) {
-                        // low planes first: the MMA warp consumes the levels in increasing order
-                        tma_load_2d(sa + p * OZ_A_TILE, &tmA, ka + c * OZ_BK, p * op.a_plane_rows + a_row, &full[stage]);
-                        tma_load_2d(sb + p * OZ_B_TILE, &tmB, kb + c * OZ_BK, p * op.b_plane_rows + b_row, &full[stage]);
+                for (int pass = 0; pass < 2; pass++) {
+                    const int npl = pass == 0 ? OZ_L0 : OZ_S;
+                    for (int c = 0; c < nch; c++) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        mbar_arrive_expect_tx(&full[stage], (uint32_t)npl * (OZ_A_TILE + OZ_B_TILE));
+                        uint8_t* sa = base + stage * OZ_STAGE_BYTES;
+                        uint8_t* sb = sa + OZ_S * OZ_A_TILE;
+                        for (int p = 0; p < npl; p++) {
+                            tma_load_2d(sa + p * OZ_A_TILE, &tmA, ka + c * OZ_BK, p * op.a_plane_rows + a_row, &full[stage]);
+                            tma_load_2d(sb + p * OZ_B_TILE, &tmB, kb + c * OZ_BK, p * op.b_plane_rows + b_row, &full[stage]);
+                        }
+                        if (++stage == OZ_STAGES) { stage = 0; phase ^= 1; }
                     }
-                    if (++stage == OZ_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -234,55 +236,77 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===== MMA issuer =====
         uint32_t stage = 0, phase = 0, tphase = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            int ti, tj, half, klo;
-            if (!oz_decode(op, item, tm, ti, tj, half)) continue;
+            int ti, tj, klo;
+            if (!oz_decode(op, item, tm, ti, tj)) continue;
             const int nch = oz_chunks(op, ti, tj, klo);
             if (nch == 0) continue;
-            mbar_wait(tmem_empty, tphase ^ 1);   // the epilogue has drained the previous item's accumulators
-            tc_fence_after();
-            for (int c = 0; c < nch; c++) {
-                mbar_wait(&full[stage], phase);
+            for (int pass = 0; pass < 2; pass++) {
+                mbar_wait(tmem_empty, tphase ^ 1);   // the epilogue has drained the previous accumulators
                 tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t sa = smem_u32(base + stage * OZ_STAGE_BYTES);
-                    const uint32_t sb = sa + OZ_S * OZ_A_TILE;
+                for (int c = 0; c < nch; c++) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t sa = smem_u32(base + stage * OZ_STAGE_BYTES);
+                        const uint32_t sb = sa + OZ_S * OZ_A_TILE;
+                        if (pass == 0) {
 #pragma unroll
-                    for (int ks = 0; ks < OZ_BK / OZ_UMMA_K; ks++) {
+                            for (int ks = 0; ks < OZ_BK / OZ_UMMA_K; ks++) {
 #pragma unroll
-                        for (int lvl = 0; lvl < OZ_S; lvl++) {
+                                for (int lvl = 0; lvl < OZ_L0; lvl++) {
 #pragma unroll
-                            for (int i = 0; i <= lvl; i++) {
-                                const int j = lvl - i;
-                                const uint64_t ad = oz_smem_desc(sa + i * OZ_A_TILE + ks * OZ_UMMA_K);
-                                const uint64_t bd = oz_smem_desc(sb + j * OZ_B_TILE + ks * OZ_UMMA_K);
-                                umma_i8(tmem_base + lvl * OZ_BN, ad, bd, OZ_IDESC, (c > 0 || ks > 0 || i > 0) ? 1u : 0u);
+                                    for (int i = 0; i <= lvl; i++) {
+                                        const int j = lvl - i;
+                                        const uint64_t ad = oz_smem_desc(sa + i * OZ_A_TILE + ks * OZ_UMMA_K);
+                                        const uint64_t bd = oz_smem_desc(sb + j * OZ_B_TILE + ks * OZ_UMMA_K);
+                                        umma_i8(tmem_base + lvl * OZ_BN, ad, bd, OZ_IDESC, (c > 0 || ks > 0 || i > 0) ? 1u : 0u);
+                                    }
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int ks = 0; ks < OZ_BK / OZ_UMMA_K; ks++) {
+#pragma unroll
+                                for (int lvl = OZ_L0; lvl < OZ_S; lvl++) {
+#pragma unroll
+                                    for (int i = 0; i <= lvl; i++) {
+                                        const int j = lvl - i;
+                                        if (i < OZ_S && j < OZ_S) {
+                                            const uint64_t ad = oz_smem_desc(sa + i * OZ_A_TILE + ks * OZ_UMMA_K);
+                                            const uint64_t bd = oz_smem_desc(sb + j * OZ_B_TILE + ks * OZ_UMMA_K);
+                                            umma_i8(tmem_base + (lvl - OZ_L0) * OZ_BN, ad, bd, OZ_IDESC,
+                                                    (c > 0 || ks > 0 || i > 0) ? 1u : 0u);
+                                        }
+                                    }
+                                }
                             }
                         }
+                        umma_commit(&empty[stage]);                 // slot reusable once these MMAs have read it
+                        if (c == nch - 1) umma_commit(tmem_full);   // accumulators of this pass complete
                     }
-                    umma_commit(&empty[stage]);                 // stage reusable once these MMAs have read it
-                    if (c == nch - 1) umma_commit(tmem_full);   // accumulators complete
+                    __syncwarp();
+                    if (++stage == OZ_STAGES) { stage = 0; phase ^= 1; }
                 }
-                __syncwarp();
-                if (++stage == OZ_STAGES) { stage = 0; phase ^= 1; }
+                tphase ^= 1;
             }
-            tphase ^= 1;
         }
     } else {
-        // ===== epilogue: TMEM lane quarter (warp % 4), one output row per thread =====
+        // ===== epilogue: TMEM lane quarter (warp % 4), one output row per thread, 64 columns per warp =====
         const int q = warp & 3;
+        const int ch = (warp - 2) >> 2;
         const int row = q * 32 + lane;
         uint32_t tphase = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            int ti, tj, half, klo;
-            if (!oz_decode(op, item, tm, ti, tj, half)) continue;
+            int ti, tj, klo;
+            if (!oz_decode(op, item, tm, ti, tj)) continue;
             const int nch = oz_chunks(op, ti, tj, klo);
-            double* Crow = op.C + (long long)z * op.c_zs + ((long long)ti * TILE + row) * op.ldc + (long long)tj * TILE +
-                           half * OZ_BN;
-            const double alpha = op.alpha, beta = op.beta;
+            double* Crow = op.C + (long long)z * op.c_zs + ((long long)ti * TILE + row) * op.ldc + (long long)tj * TILE + ch * 64;
+            const double alpha = op.alpha;
             if (nch == 0) {
                 // empty K range: C <- beta C
+                const double beta = op.beta;
 #pragma unroll 4
-                for (int c = 0; c < OZ_BN; c += 2) {
+                for (int c = 0; c < 64; c += 2) {
                     double2* p2 = reinterpret_cast<double2*>(Crow + c);
                     double2 o = make_double2(0.0, 0.0);
                     if (beta != 0.0) { o = *p2; o.x *= beta; o.y *= beta; }
@@ -290,50 +314,62 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 continue;
             }
-            const double sa = alpha * op.a_scale[op.a_row0 + z * op.a_zs_row + ti * TILE + row] * (1.0 / 65536.0);
-            const double* sbp = op.b_scale + op.b_row0 + z * op.b_zs_row + tj * TILE + half * OZ_BN;
-            // C and the column scales of a 16-column group are fetched before the accumulators are read (for the
-            // first group: before the item's MMAs have finished), so that their latency is not paid per element
-            double2 old[8], sb2[8];
-            auto prefetch = [&](int cg) {
+            const double sa0 = alpha * op.a_scale[op.a_row0 + z * op.a_zs_row + ti * TILE + row];
+            const double* sbp = op.b_scale + op.b_row0 + z * op.b_zs_row + tj * TILE + ch * 64;
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + ch * 64;
+            for (int pass = 0; pass < 2; pass++) {
+                const double beta = pass == 0 ? op.beta : 1.0;
+                // 256^-(lvl+2) of the pass's lowest level: 2^-16 (pass 0), 2^-48 (pass 1)
+                const double sa = sa0 * (pass == 0 ? (1.0 / 65536.0) : (1.0 / 281474976710656.0));
+                // C and the column scales of a 16-column group are fetched before the accumulators are read (for the
+                // first group: before the pass's MMAs have finished), so that their latency is not paid per element
+                double2 old[8], sb2[8];
+                auto prefetch = [&](int cg) {
 #pragma unroll
-                for (int e = 0; e < 8; e++) {
-                    sb2[e] = *reinterpret_cast<const double2*>(sbp + cg * 16 + 2 * e);
-                    old[e] = (beta != 0.0) ? *reinterpret_cast<const double2*>(Crow + cg * 16 + 2 * e)
-                                           : make_double2(0.0, 0.0);
-                }
-            };
-            prefetch(0);
-            mbar_wait(tmem_full, tphase);
-            tc_fence_after();
-            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-            for (int cg = 0; cg < OZ_BN / 16; cg++) {
-                int v[OZ_S][16];
-#pragma unroll
-                for (int lvl = 0; lvl < OZ_S; lvl++) tmem_ld16(trow + lvl * OZ_BN + cg * 16, v[lvl]);
-                tmem_ld_wait();
-                double2 o[8];
-#pragma unroll
-                for (int e = 0; e < 8; e++) {
-                    double s0 = (double)v[OZ_S - 1][2 * e], s1 = (double)v[OZ_S - 1][2 * e + 1];
-#pragma unroll
-                    for (int lvl = OZ_S - 2; lvl >= 0; lvl--) {
-                        s0 = fma(s0, 1.0 / 256.0, (double)v[lvl][2 * e]);
-                        s1 = fma(s1, 1.0 / 256.0, (double)v[lvl][2 * e + 1]);
+                    for (int e = 0; e < 8; e++) {
+                        sb2[e] = *reinterpret_cast<const double2*>(sbp + cg * 16 + 2 * e);
+                        old[e] = (beta != 0.0) ? *reinterpret_cast<const double2*>(Crow + cg * 16 + 2 * e)
+                                               : make_double2(0.0, 0.0);
                     }
-                    o[e].x = fma(beta, old[e].x, s0 * sa * sb2[e].x);
-                    o[e].y = fma(beta, old[e].y, s1 * sa * sb2[e].y);
-                }
-                double* dst = Crow + cg * 16;
-                if (cg + 1 < OZ_BN / 16) prefetch(cg + 1);
+                };
+                prefetch(0);
+                mbar_wait(tmem_full, tphase);
+                tc_fence_after();
+#pragma unroll 1
+                for (int cg = 0; cg < 4; cg++) {
+                    int v[OZ_L0][16];
+                    if (pass == 0) {
 #pragma unroll
-                for (int e = 0; e < 8; e++) *reinterpret_cast<double2*>(dst + 2 * e) = o[e];
+                        for (int a = 0; a < OZ_L0; a++) tmem_ld16(trow + a * OZ_BN + cg * 16, v[a]);
+                    } else {
+#pragma unroll
+                        for (int a = 0; a < OZ_S - OZ_L0; a++) tmem_ld16(trow + a * OZ_BN + cg * 16, v[a]);
+#pragma unroll
+                        for (int e = 0; e < 16; e++) v[OZ_L0 - 1][e] = 0;
+                    }
+                    tmem_ld_wait();
+                    double2 o[8];
+#pragma unroll
+                    for (int e = 0; e < 8; e++) {
+                        double s0 = (double)v[OZ_L0 - 1][2 * e], s1 = (double)v[OZ_L0 - 1][2 * e + 1];
+#pragma unroll
+                        for (int a = OZ_L0 - 2; a >= 0; a--) {
+                            s0 = fma(s0, 1.0 / 256.0, (double)v[a][2 * e]);
+                            s1 = fma(s1, 1.0 / 256.0, (double)v[a][2 * e + 1]);
+                        }
+                        o[e].x = fma(beta, old[e].x, s0 * sa * sb2[e].x);
+                        o[e].y = fma(beta, old[e].y, s1 * sa * sb2[e].y);
+                    }
+                    double* dst = Crow + cg * 16;
+#pragma unroll
+                    for (int e = 0; e < 8; e++) *reinterpret_cast<double2*>(dst + 2 * e) = o[e];
+                    if (cg + 1 < 4) prefetch(cg + 1);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tmem_empty);
+                tphase ^= 1;
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty);
-            tphase ^= 1;
         }
     }
     tc_fence_before();
@@ -377,10 +413,10 @@ inline cudaError_t oz_set_attributes() {
     return cudaFuncSetAttribute(oz_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES);
 }
 
-// items_per_cta: CTAs are NOT persistent over the whole launch -- each handles about this many 128x64 items
+// items_per_cta: CTAs are NOT persistent over the whole launch -- each handles about this many 128x128 tiles
 // (grid-stride), so that SMs are handed back every few items and higher-priority streams (the panel chain of the
 // factorisation) get in; the hardware block scheduler does the load balancing.
-inline int g_oz_items_per_cta = 2;
+inline int g_oz_items_per_cta = 1;
 
 inline cudaError_t launch_oz_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const OzGemmOp& op_in, int nbatch,
                                   cudaStream_t st, int items_per_cta = 0) {
@@ -389,7 +425,7 @@ inline cudaError_t launch_oz_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB
     else op.n_tiles = op.tiles_m * op.tiles_n;
     if (op.n_tiles <= 0 || nbatch <= 0) return cudaSuccess;
     const int ipc = items_per_cta > 0 ? items_per_cta : g_oz_items_per_cta;
-    int gx = (op.n_tiles * 2 + ipc - 1) / ipc;
+    int gx = (op.n_tiles + ipc - 1) / ipc;
     if (gx < 1) gx = 1;
     count_launch();
     oz_gemm_kernel<<<dim3(gx, nbatch), OZ_THREADS, OZ_SMEM_BYTES, st>>>(tmA, tmB, op);

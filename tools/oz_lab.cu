@@ -406,11 +406,96 @@ static void perf(int n, int kblocks, int tri, int reps) {
     free_planes(P);
 }
 
+
+// ---- raw tcgen05 kind::i8 issue rate: one CTA per SM, MMAs back to back on resident shared-memory tiles ----------
+template <int N, int KB>
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int iters, int a_tiles, int b_tiles, long long* cycles) {
+    extern __shared__ uint8_t raw[];
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t bar;
+    __shared__ uint32_t slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < (a_tiles * 128 * KB + b_tiles * N * KB) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(base)[i] = 0x01010101u;
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc(&slot, 512);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tm = slot;
+    constexpr uint64_t layout = (KB == 128) ? 2 : (KB == 64 ? 4 : 6);
+    constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    if (warp == 1 && lane == 0) {
+        const uint32_t sa = smem_u32(base), sb = sa + a_tiles * 128 * KB;
+        const long long t0 = clock64();
+        const int nacc = 512 / N;
+        const uint64_t hi = ((uint64_t)((8 * KB) >> 4) << 32) | (1ull << 46) | (layout << 61);
+        for (int it = 0; it < iters; it += 8) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                // operand tiles rotate with compile-time offsets; a_tiles / b_tiles are powers of two or 7 (masked to < 8)
+                const int ia = (u * 3) % 8 < a_tiles ? (u * 3) % 8 : 0, ib = (u * 5) % 8 < b_tiles ? (u * 5) % 8 : 0;
+#pragma unroll
+                for (int ks = 0; ks < KB / 32; ks++) {
+                    const uint64_t ad = (uint64_t)(((sa + ia * 128 * KB + ks * 32) & 0x3FFFF) >> 4) | hi;
+                    const uint64_t bd = (uint64_t)(((sb + ib * N * KB + ks * 32) & 0x3FFFF) >> 4) | hi;
+                    umma_i8(tm + (u % nacc) * N, ad, bd, idesc, 1u);
+                }
+            }
+        }
+        umma_commit(&bar);
+        mbar_wait(&bar, 0);
+        const long long t1 = clock64();
+        if (blockIdx.x == 0) cycles[0] = t1 - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tm, 512);
+}
+
+template <int N, int KB>
+static void mma_rate(int a_tiles, int b_tiles) {
+    long long* dc;
+    CHECK(cudaMalloc(&dc, 8));
+    const int smem = a_tiles * 128 * KB + b_tiles * N * KB + 2048;
+    CHECK(cudaFuncSetAttribute(mma_rate_kernel<N, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int iters = 8192;
+    mma_rate_kernel<N, KB><<<148, 128, smem>>>(iters, a_tiles, b_tiles, dc);
+    CHECK(cudaDeviceSynchronize());
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    mma_rate_kernel<N, KB><<<148, 128, smem>>>(iters, a_tiles, b_tiles, dc);
+    cudaEventRecord(e1);
+    CHECK(cudaEventSynchronize(e1));
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    long long cyc; CHECK(cudaMemcpy(&cyc, dc, 8, cudaMemcpyDeviceToHost));
+    const double nm = (double)iters * (KB / 32);
+    printf("i8 MMA M=128 N=%d (K chunk %d B, %d A tiles, %d B tiles): %.1f cycles per MMA (ideal %.1f), %.0f TOPS on 148 SMs\n", N, KB,
+           a_tiles, b_tiles, (double)cyc / nm, 128.0 * N * 32 / 7736.0 * 1.0, 148.0 * nm * 2.0 * 128 * N * 32 / (ms * 1e-3) * 1e-12);
+    fflush(stdout);
+    cudaFree(dc);
+}
+
 int main(int argc, char** argv) {
     const char* what = argc > 1 ? argv[1] : "all";
     int fails = 0;
     CHECK(oz_set_attributes());
     CHECK(gemm_set_attributes());
+    if (!strcmp(what, "rate")) {
+        mma_rate<64, 64>(7, 7);
+        mma_rate<64, 64>(1, 1);
+        mma_rate<128, 64>(7, 7);
+        mma_rate<128, 64>(1, 1);
+        mma_rate<256, 64>(4, 4);
+        mma_rate<256, 64>(1, 1);
+        mma_rate<64, 128>(4, 4);
+        mma_rate<128, 128>(4, 4);
+        mma_rate<256, 128>(2, 2);
+        mma_rate<64, 32>(7, 7);
+        mma_rate<128, 32>(7, 7);
+        return 0;
+    }
     if (!strcmp(what, "check") || !strcmp(what, "all")) {
         fails += check_small();
         fails += check_lauum(512);
