@@ -338,7 +338,10 @@ def run_ours(args):
                 "counted separately (a failed rung costs covariance + factorisation only: the status is read back "
                 "before the inverse / K^-1 / gradient are enqueued)"}
 
-    # ---- roofline of the dominant kernel (dgemm_dmma_kernel: Cholesky trailing updates, L^-1, K^-1) --------
+    # ---- roofline of the dominant kernel -------------------------------------------------------------------------
+    # The three O(N^3) stages (factorisation trailing updates, L^-1, K^-1) run either on the INT8-sliced tcgen05 GEMM
+    # (oz_gemm_kernel; default from N = 4096) or on the FP64 DMMA GEMM (dgemm_dmma_kernel; GPP_FP64=dmma).
+    fp64_mode = eng.fp64_mode()
     peak = measure_fp64_peak(local)
     n3 = float(n) ** 3
     tensor_ms = stage["cholesky"] + stage["trtri"] + stage["lauum"]
@@ -347,24 +350,17 @@ def run_ours(args):
         for k in ("cholesky", "trtri", "lauum", "covariance", "gradient"):
             stage[k] = stage[k] or float("nan")
     achieved = n3 / (tensor_ms * 1e-3) / 1e12  # N^3/3 (potrf) + N^3/3 (trtri) + N^3/3 (lauum) algorithmic flops
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "dgemm_traffic.json")
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
-    roofline = {
-        "bound": "tensor", "kernel": "dgemm_dmma_kernel (FP64 DMMA m8n8k4)", "achieved": achieved, "peak": peak,
-        "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-        "peak_source": "measured live: torch.matmul f64 8192^3 best of 10 (cuBLAS); MEASURED_PEAKS.json has no FP64 entry",
-        "algorithmic_flops_per_eval": n3,
-        "basis": "all launches of the kernel in one step: N^3 algorithmic flops (potrf + trtri + lauum, N^3/3 each) over "
-                 "the CUDA-event time of those three stages (leaf kernels and launch gaps included); `traffic` is the "
-                 "ncu DRAM read+write of the single largest launch (LAUUM, N^3/3 flops), see profiles/dgemm_traffic.json",
-        "largest_launch": {"what": "LAUUM K^-1 = L^-T L^-1, one launch", "algorithmic_flops": n3 / 3,
-                           "ms": stage["lauum"], "achieved": n3 / 3 / (stage["lauum"] * 1e-3) / 1e12,
-                           "frac": n3 / 3 / (stage["lauum"] * 1e-3) / 1e12 / peak},
+
+    def _traffic(name):
+        tpath = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tpath):
+            try:
+                return json.load(open(tpath)).get("dram_bytes_per_launch")
+            except Exception:
+                return None
+        return None
+
+    stage_extra = {
         "stages_ms": stage,
         # the leading part of L^-1 runs on a low-priority stream behind the factorisation (trtri_early), so the
         # event split between "cholesky" and "trtri" is not a split of work; their sum is (GPP_OVERLAP_INV=0
@@ -374,6 +370,75 @@ def run_ours(args):
         "hbm_stage_gbs": {"covariance": 4.0 * n * (n + 1) / (stage["covariance"] * 1e-3) / 1e9,
                           "gradient": 4.0 * n * (n + 1) / (stage["gradient"] * 1e-3) / 1e9},
     }
+    if fp64_mode == E.FP64_INT8:
+        peak_i8 = E.probe_i8(256, 4096, local)     # raw tcgen05 kind::i8 issue rate, whole GPU, measured live
+        peak_i8_n128 = E.probe_i8(128, 4096, local)
+        pairs = 28.0                                # int8 multiply-adds per FP64-equivalent multiply-add
+        ach_i8 = pairs * n3 / (tensor_ms * 1e-3) / 1e12
+        roofline = {
+            "bound": "tensor", "kernel": "oz_gemm_kernel (tcgen05.mma kind::i8 M=N=128 K=32, TMA-fed, int32 TMEM "
+                                         "accumulators; 7 digit planes per operand, 28 plane pairs)",
+            "achieved": ach_i8, "peak": peak_i8, "unit": "TOP/s (int8)", "frac": ach_i8 / peak_i8,
+            "traffic": _traffic("oz_gemm_traffic.json"),
+            "peak_source": "measured live: gpp_probe_i8 (tcgen05.mma kind::i8 M=128 N=256 issued back to back on "
+                           "resident operands, 148 SMs); the N=128 shape the kernel uses issues at %.0f TOP/s; "
+                           "MEASURED_PEAKS.json has no INT8 entry (nominal 4500)" % peak_i8_n128,
+            "algorithmic_ops_per_eval": pairs * n3,
+            "basis": "all O(N^3) work of one step: N^3 FP64-equivalent flops (potrf + trtri + lauum, N^3/3 each) = 28 N^3 "
+                     "int8 ops, over the CUDA-event time of those three stages (digit-plane splits, DMMA panel chain, "
+                     "leaf kernels and launch gaps included)",
+            "largest_launch": {"what": "K^-1 = L^-T L^-1: transposed digit-plane split + one oz_gemm launch",
+                               "algorithmic_ops": pairs * n3 / 3, "ms": stage["lauum"],
+                               "achieved": pairs * n3 / 3 / (stage["lauum"] * 1e-3) / 1e12,
+                               "frac": pairs * n3 / 3 / (stage["lauum"] * 1e-3) / 1e12 / peak_i8},
+            "fp64_equivalent": {"achieved_tflops": achieved, "fp64_tensor_peak_tflops": peak,
+                                "ratio_to_fp64_tensor_peak": achieved / peak,
+                                "peak_source": "torch.matmul f64 8192^3 best of 10 (cuBLAS DGEMM), measured live"},
+        }
+    else:
+        roofline = {
+            "bound": "tensor", "kernel": "dgemm_dmma_kernel (FP64 DMMA m8n8k4)", "achieved": achieved, "peak": peak,
+            "unit": "TFLOP/s", "frac": achieved / peak, "traffic": _traffic("dgemm_traffic.json"),
+            "peak_source": "measured live: torch.matmul f64 8192^3 best of 10 (cuBLAS); MEASURED_PEAKS.json has no FP64 entry",
+            "algorithmic_flops_per_eval": n3,
+            "basis": "all launches of the kernel in one step: N^3 algorithmic flops (potrf + trtri + lauum, N^3/3 each) over "
+                     "the CUDA-event time of those three stages (leaf kernels and launch gaps included); `traffic` is the "
+                     "ncu DRAM read+write of the single largest launch (LAUUM, N^3/3 flops), see profiles/dgemm_traffic.json",
+            "largest_launch": {"what": "LAUUM K^-1 = L^-T L^-1, one launch", "algorithmic_flops": n3 / 3,
+                               "ms": stage["lauum"], "achieved": n3 / 3 / (stage["lauum"] * 1e-3) / 1e12,
+                               "frac": n3 / 3 / (stage["lauum"] * 1e-3) / 1e12 / peak},
+        }
+    roofline.update(stage_extra)
+
+    # ---- the exact-DMMA arm of the same evaluation (IEEE FP64 products on mma.sync), rank 0, outside the timed region ----
+    exact_dmma = None
+    if fp64_mode == E.FP64_INT8 and not args.no_dmma_arm:
+        model.release_engine()
+        eng = None
+        prev = E.set_fp64_mode(E.FP64_DMMA)
+        try:
+            eng2 = model._get_engine()
+            eng2.mll_grad(W.c4_natural(thetas[2]), want_grad=True)
+            res2, tms, st2 = {}, [], {k: 0.0 for k in ("cholesky", "trtri", "lauum")}
+            for k in (1, 0, 2):
+                res2[k] = eng2.mll_grad(W.c4_natural(thetas[k]), want_grad=True)
+                tm = eng2.timings()
+                tms.append(tm["total"])
+                for q in st2:
+                    st2[q] += tm[q] / 3.0
+            par2 = check_parity(n, res2)
+            t2 = sum(st2.values())
+            exact_dmma = {"ms_per_step": statistics.median(tms), "value": 1e3 / statistics.median(tms), "unit": "evals/s",
+                          "steps": 3, "parity": {"rel_nll": par2["rel_nll"], "rel_grad": par2["rel_grad"]},
+                          "roofline": {"kernel": "dgemm_dmma_kernel (FP64 DMMA m8n8k4)", "achieved": n3 / (t2 * 1e-3) / 1e12,
+                                       "peak": peak, "unit": "TFLOP/s", "frac": n3 / (t2 * 1e-3) / 1e12 / peak,
+                                       "stages_ms": st2},
+                          "int8_vs_dmma_rel_nll": abs(res2[1]["nll"] - first_out["nll"]) / abs(res2[1]["nll"]),
+                          "note": "same engine with GPP_FP64=dmma (gpp_set_fp64_mode(0)): every product in IEEE FP64 on the "
+                                  "DMMA tensor cores; device ms per evaluation from CUDA events"}
+        finally:
+            E.set_fp64_mode(prev)
+            model.release_engine()
 
     # ---- CPU baseline: the oracle on this box's host cores, ONE real full-size evaluation (N=1 runs only) ----
     cpu = None
@@ -390,6 +455,10 @@ def run_ours(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps,
         "device_ms_per_step": 1e3 * device_elapsed / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "fp64_arithmetic": ("int8-sliced: FP64 operands cut into 7 signed base-256 digit planes per power-of-two-scaled row, "
+                            "exact integer products on tcgen05 kind::i8, FP64 recombination and accumulation (results "
+                            "within 1e-12 of the DMMA arm, see parity / exact_dmma)") if fp64_mode == E.FP64_INT8
+        else "IEEE FP64 products on DMMA (mma.sync m8n8k4)",
         "config": bench_config(n),
         "parallelism": "independent restarts, one per GPU (no data-path collective)",
         "nll_first_step": first_out["nll"],
@@ -404,6 +473,7 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "parity": parity,
         "prior_draws": prior_draws,
+        "exact_dmma": exact_dmma,
         "extra": extra,
     }
     print(json.dumps(line), flush=True)
@@ -690,6 +760,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true",
                     help="mll workload: skip extra.fit_c2 / extra.acq_c5 (the sharded workloads of the metric's second half)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="mll workload: skip the full-size CPU oracle evaluation")
+    ap.add_argument("--no-dmma-arm", action="store_true", help="mll workload: skip the exact-DMMA arm of the same evaluation")
     ap.add_argument("--no-prior-sweep", action="store_true",
                     help="mll workload: skip the untimed sweep over all 65 prior draws (profiling runs)")
     args = ap.parse_args()

@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -121,7 +122,15 @@ static const double* hyp_beta(const gpp_handle* h) { return h->hyp + h->dq + zta
 static const double* hyp_sf2(const gpp_handle* h) { return hyp_beta(h) + h->n_mean; }
 static const double* hyp_jitter(const gpp_handle* h) { return hyp_beta(h) + h->n_mean + 1; }
 
-extern "C" int gpp_version(void) { return 105; }
+extern "C" int gpp_version(void) { return 106; }
+
+// process-wide default for handles created afterwards: -1 = by size (INT8-sliced from Np = 4096), 0 = DMMA, 1 = INT8
+static std::atomic<int> g_fp64_mode{-1};
+extern "C" int gpp_set_fp64_mode(int mode) {
+    if (mode < -1 || mode > 1) return g_fp64_mode.load();
+    return g_fp64_mode.exchange(mode);
+}
+extern "C" int gpp_get_fp64_mode(gpp_handle* h) { return (h && h->oz && h->oz->ready) ? GPP_FP64_INT8 : GPP_FP64_DMMA; }
 
 extern "C" int gpp_device_count(void) {
     int c = 0;
@@ -390,7 +399,10 @@ extern "C" int gpp_create(const gpp_problem* p, int device, gpp_handle** out) {
         // (below that the stages are latency-bound and the DMMA kernels win); GPP_FP64=dmma keeps everything on DMMA
         const char* e = getenv("GPP_FP64");
         bool int8 = h->T >= 32;
-        if (e) int8 = int8 && strcmp(e, "dmma") != 0;
+        const int mode = g_fp64_mode.load();
+        if (mode == GPP_FP64_DMMA) int8 = false;
+        if (mode == GPP_FP64_INT8) int8 = h->T >= 8;   // forced: the stages still pick DMMA for shapes that are too small
+        if (e && mode < 0) int8 = int8 && strcmp(e, "dmma") != 0;
         if (int8) {
             h->oz = new OzCtx();
             if ((e = getenv("GPP_OZ_MIN_TRAIL")) != nullptr) h->oz->min_trailing_tiles = atoi(e);
@@ -1372,5 +1384,15 @@ extern "C" int gpp_probe_dgemm(int device, int m, int n, int k, int iters, float
     cudaFree(A);
     cudaFree(B);
     cudaFree(C);
+    return GPP_OK;
+}
+
+extern "C" int gpp_probe_i8(int device, int n_cols, int iters, double* tops_out) {
+    if (!tops_out || iters <= 0 || (n_cols != 64 && n_cols != 128 && n_cols != 256)) ARG_FAIL("gpp_probe_i8: bad arguments");
+    CK(cudaSetDevice(device));
+    iters = (iters + 7) / 8 * 8;
+    if (n_cols == 64) CK(oz_probe_rate_n<64>(iters, tops_out));
+    else if (n_cols == 128) CK(oz_probe_rate_n<128>(iters, tops_out));
+    else CK(oz_probe_rate_n<256>(iters, tops_out));
     return GPP_OK;
 }

@@ -432,6 +432,81 @@ inline cudaError_t launch_oz_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB
     return cudaGetLastError();
 }
 
+
+// ---- raw tcgen05 kind::i8 issue rate (the roofline denominator of this kernel family) -----------------------------
+// One CTA per SM, M = 128 MMAs of width N issued back to back on resident shared-memory tiles (no TMA traffic).
+template <int N>
+__global__ void __launch_bounds__(128, 1) oz_mma_rate_kernel(int iters) {
+    extern __shared__ uint8_t oz_rate_raw[];
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(oz_rate_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t bar;
+    __shared__ uint32_t slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int TILES = 4;
+    for (int i = threadIdx.x; i < TILES * (128 + N) * 64 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(base)[i] = 0x01ff02feu;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(&slot, 512);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tm = slot;
+    constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    if (warp == 1 && lane == 0) {
+        const uint32_t sa = smem_u32(base), sb = sa + TILES * 128 * 64;
+        constexpr int nacc = 512 / N;
+        const uint64_t hi = ((uint64_t)((8 * 64) >> 4) << 32) | (1ull << 46) | (4ull << 61);
+        for (int it = 0; it < iters; it += 8) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int ia = (u * 3) % TILES, ib = (u * 5) % TILES;
+#pragma unroll
+                for (int ks = 0; ks < 2; ks++) {
+                    const uint64_t ad = (uint64_t)(((sa + ia * 128 * 64 + ks * 32) & 0x3FFFF) >> 4) | hi;
+                    const uint64_t bd = (uint64_t)(((sb + ib * N * 64 + ks * 32) & 0x3FFFF) >> 4) | hi;
+                    umma_i8(tm + (u % nacc) * N, ad, bd, idesc, 1u);
+                }
+            }
+        }
+        umma_commit(&bar);
+        mbar_wait(&bar, 0);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tm, 512);
+}
+
+// int8 tera-ops per second of the whole GPU for MMA width n (64, 128 or 256); 2 * 128 * n * 32 ops per MMA
+template <int N>
+inline cudaError_t oz_probe_rate_n(int iters, double* tops) {
+    constexpr int smem = 4 * (128 + N) * 64 + 2048;
+    cudaError_t e = cudaFuncSetAttribute(oz_mma_rate_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    oz_mma_rate_kernel<N><<<GEMM_NUM_SMS, 128, smem>>>(iters);
+    double best = 0.0;
+    for (int rep = 0; rep < 3; rep++) {
+        cudaEventRecord(e0);
+        oz_mma_rate_kernel<N><<<GEMM_NUM_SMS, 128, smem>>>(iters);
+        cudaEventRecord(e1);
+        e = cudaEventSynchronize(e1);
+        if (e != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double t = (double)GEMM_NUM_SMS * iters * 2.0 * (2.0 * 128.0 * N * 32.0) / (ms * 1e-3) * 1e-12;
+        if (t > best) best = t;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tops = best;
+    return e;
+}
+
 inline OzGemmOp oz_default() {
     OzGemmOp op{};
     op.alpha = 1.0;

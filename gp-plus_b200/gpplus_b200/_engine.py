@@ -23,7 +23,7 @@ EXPORTS = (
     "gpp_version", "gpp_device_count", "gpp_last_error", "gpp_launch_count", "gpp_create", "gpp_destroy", "gpp_pool_clear",
     "gpp_mll_grad",
     "gpp_get_timings", "gpp_get_stats", "gpp_covariance", "gpp_fetch", "gpp_factorize", "gpp_predict", "gpp_acq_argmax",
-    "gpp_probe_dgemm", "gpp_set_theta_layout", "gpp_objective", "gpp_objective_enqueue", "gpp_objective_collect",
+    "gpp_probe_dgemm", "gpp_probe_i8", "gpp_set_fp64_mode", "gpp_get_fp64_mode", "gpp_set_theta_layout", "gpp_objective", "gpp_objective_enqueue", "gpp_objective_collect",
 )
 
 PRIOR_NORMAL, PRIOR_LOGNORMAL_OS, PRIOR_HORSESHOE, PRIOR_MOLLIFIED, PRIOR_CONST = 0, 1, 2, 3, 4
@@ -129,6 +129,12 @@ def load_library():
         lib.gpp_acq_argmax.restype = C.c_int
         lib.gpp_probe_dgemm.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
         lib.gpp_probe_dgemm.restype = C.c_int
+        lib.gpp_probe_i8.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
+        lib.gpp_probe_i8.restype = C.c_int
+        lib.gpp_set_fp64_mode.argtypes = [C.c_int]
+        lib.gpp_set_fp64_mode.restype = C.c_int
+        lib.gpp_get_fp64_mode.argtypes = [C.c_void_p]
+        lib.gpp_get_fp64_mode.restype = C.c_int
         lib.gpp_set_theta_layout.argtypes = [C.c_void_p, C.POINTER(_ThetaLayout)]
         lib.gpp_set_theta_layout.restype = C.c_int
         lib.gpp_objective.argtypes = [C.c_void_p, C.c_void_p, C.c_int, _dp, C.c_void_p, C.POINTER(_MllResult)]
@@ -368,6 +374,10 @@ class Engine:
             _raise(rc, "gpp_get_timings")
         return {k: float(getattr(t, k)) for k, _ in _Timings._fields_}
 
+    def fp64_mode(self) -> int:
+        """FP64_DMMA or FP64_INT8: the arithmetic this handle uses for the O(N^3) stages (gpp_get_fp64_mode)."""
+        return int(self._lib.gpp_get_fp64_mode(self._h))
+
     def stats(self) -> Dict[str, int]:
         st = _Stats()
         rc = self._lib.gpp_get_stats(self._h, C.byref(st))
@@ -452,3 +462,21 @@ def probe_dgemm(m: int, n: int, k: int, iters: int = 10, device: int = 0) -> flo
     if rc != GPP_OK:
         _raise(rc, "gpp_probe_dgemm")
     return float(ms.value)
+
+
+FP64_DMMA, FP64_INT8 = 0, 1
+
+
+def set_fp64_mode(mode: int) -> int:
+    """Arithmetic of the O(N^3) stages for engines created afterwards: -1 by size (default), FP64_DMMA, FP64_INT8
+    (include/gpplus_b200.h).  Returns the previous setting."""
+    return int(load_library().gpp_set_fp64_mode(int(mode)))
+
+
+def probe_i8(n_cols: int = 256, iters: int = 4096, device: int = 0) -> float:
+    """Raw tcgen05 kind::i8 issue rate of the GPU in int8 tera-ops per second (gpp_probe_i8)."""
+    tops = C.c_double(0.0)
+    rc = load_library().gpp_probe_i8(device, n_cols, iters, C.byref(tops))
+    if rc != 0:
+        _raise(rc, "gpp_probe_i8")
+    return float(tops.value)

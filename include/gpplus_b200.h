@@ -231,6 +231,23 @@ int gpp_objective(gpp_handle* h, const double* theta, int want_grad, double* val
 int gpp_objective_enqueue(gpp_handle* h, const double* theta, int want_grad);
 int gpp_objective_collect(gpp_handle* h, double* value, double* grad, gpp_mll_result* detail);
 
+/* Arithmetic of the three O(N^3) stages (factorisation trailing updates, triangular inverse, K^-1).  Both produce
+ * FP64 results within the parity tolerances (objective 1e-9, gradient 1e-8; observed 2e-13 / 3e-13 at N = 16384):
+ *   GPP_FP64_DMMA  mma.sync FP64 tensor-core tiles (IEEE FP64 products and sums)
+ *   GPP_FP64_INT8  operands cut into 7 signed base-256 digit planes per power-of-two-scaled row, exact integer products
+ *                  on the INT8 tcgen05 tensor cores, FP64 recombination (csrc/oz_gemm.cuh).  Default from N = 4096.
+ * gpp_set_fp64_mode sets the process-wide choice for handles created afterwards (-1 = by size, the default;
+ * the environment variable GPP_FP64=dmma has the same effect as 0) and returns the previous one;
+ * gpp_get_fp64_mode reports what a handle uses. */
+#define GPP_FP64_DMMA 0
+#define GPP_FP64_INT8 1
+int gpp_set_fp64_mode(int mode);
+int gpp_get_fp64_mode(gpp_handle* h);
+
+/* raw issue rate of tcgen05.mma kind::i8 (M = 128, N = n_cols in {64, 128, 256}) on resident operands, whole GPU,
+ * in int8 tera-ops per second: the roofline denominator of the INT8-sliced path (bench.py measures it live) */
+int gpp_probe_i8(int device, int n_cols, int iters, double* tops_out);
+
 /* FP64 DMMA GEMM probe used by bench/selftest: C[m x n] = A[m x k] * B[n x k]^T on device
  * scratch, returns average milliseconds per launch over iters (m,n,k multiples of 128). */
 int gpp_probe_dgemm(int device, int m, int n, int k, int iters, float* ms_out);

@@ -26,6 +26,10 @@ def summarise(path):
         for w in WANT:
             if w in idx:
                 d[w] = "%s %s" % (r[idx[w]], units[idx[w]])
+        for name, i in idx.items():   # every tensor-pipe / TMEM / cache-throughput metric of the capture
+            if name not in d and any(t in name for t in ("pipe_tensor", "tmem", "lts__throughput", "l1tex__throughput",
+                                                          "sm__inst_executed_pipe_uniform", "shared_op")):
+                d[name] = "%s %s" % (r[i], units[i])
         out.append(d)
     return out
 
