@@ -25,8 +25,9 @@
 //                      2-slot mbarrier ring
 //   warp 1 (one lane)  tcgen05.mma.cta_group::1.kind::i8, M = N = 128, K = 32; tcgen05.commit frees the slot /
 //                      publishes the accumulators
-//   warps 2-9          epilogue: tcgen05.ld (TMEM lane = output row; two warps per lane quarter, 64 columns each),
-//                      Horner over the levels in FP64, power-of-two row / column scales, read-modify-write of C
+//   warps 2-9          epilogue: tcgen05.ld 16x256b (two warps per TMEM lane quarter, 64 columns each; a quad of threads
+//                      owns 64 contiguous bytes of a C row), Horner over the levels in FP64, power-of-two row /
+//                      column scales, read-modify-write of C in full 32-byte sectors
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -72,6 +73,8 @@ struct OzGemmOp {
     int klo_sel, klo_c, khi_sel, khi_c;
     double alpha, beta;
     int n_tiles;                     // 128x128 tiles per batch entry (set by launch_oz_gemm)
+    long long* prof;                 // optional (development): clock64 stamps of CTA 0's first item, 4 per pass:
+                                     // accumulators free, MMAs issued, accumulators complete, epilogue done
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------
@@ -116,6 +119,17 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&v)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+// 16 TMEM lanes x 32 columns: register 4j + {0,1} = lane (base + laneid / 4), columns 8j + 2 (laneid % 4) + {0,1};
+// register 4j + {2,3} = the same columns of lane (base + 8 + laneid / 4)   (cute SM100_TMEM_LOAD_16dp256b4x layout).
+// A quad of threads therefore holds 8 consecutive columns of a row: 64 contiguous bytes once converted to FP64.
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, int (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
           "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr)
@@ -243,6 +257,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int pass = 0; pass < 2; pass++) {
                 mbar_wait(tmem_empty, tphase ^ 1);   // the epilogue has drained the previous accumulators
                 tc_fence_after();
+                if (op.prof && blockIdx.x == 0 && z == 0 && item == 0 && lane == 0) op.prof[pass * 4 + 0] = clock64();
                 for (int c = 0; c < nch; c++) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
@@ -287,87 +302,112 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     __syncwarp();
                     if (++stage == OZ_STAGES) { stage = 0; phase ^= 1; }
                 }
+                if (op.prof && blockIdx.x == 0 && z == 0 && item == 0 && lane == 0) op.prof[pass * 4 + 1] = clock64();
                 tphase ^= 1;
             }
         }
     } else {
-        // ===== epilogue: TMEM lane quarter (warp % 4), one output row per thread, 64 columns per warp =====
+        // ===== epilogue: TMEM lane quarter (warp % 4), 64 columns per warp; 16-lane x 32-column loads whose fragment
+        // layout gives every quad of threads 64 contiguous bytes of a C row (full 32-byte sectors both ways) =====
         const int q = warp & 3;
         const int ch = (warp - 2) >> 2;
-        const int row = q * 32 + lane;
+        const int r_in = lane >> 2, cq = (lane & 3) * 2;
         uint32_t tphase = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             int ti, tj, klo;
             if (!oz_decode(op, item, tm, ti, tj)) continue;
             const int nch = oz_chunks(op, ti, tj, klo);
-            double* Crow = op.C + (long long)z * op.c_zs + ((long long)ti * TILE + row) * op.ldc + (long long)tj * TILE + ch * 64;
+            // this thread's first element of the tile: row q*32 + r_in, column ch*64 + cq
+            double* C0 = op.C + (long long)z * op.c_zs + ((long long)ti * TILE + q * 32 + r_in) * op.ldc + (long long)tj * TILE +
+                         ch * 64 + cq;
             const double alpha = op.alpha;
             if (nch == 0) {
                 // empty K range: C <- beta C
                 const double beta = op.beta;
-#pragma unroll 4
-                for (int c = 0; c < 64; c += 2) {
-                    double2* p2 = reinterpret_cast<double2*>(Crow + c);
-                    double2 o = make_double2(0.0, 0.0);
-                    if (beta != 0.0) { o = *p2; o.x *= beta; o.y *= beta; }
-                    *p2 = o;
-                }
+                for (int rr = 0; rr < 4; rr++)
+                    for (int j = 0; j < 8; j++) {
+                        double2* p2 = reinterpret_cast<double2*>(C0 + (long long)rr * 8 * op.ldc + 8 * j);
+                        double2 o = make_double2(0.0, 0.0);
+                        if (beta != 0.0) { o = *p2; o.x *= beta; o.y *= beta; }
+                        *p2 = o;
+                    }
                 continue;
             }
-            const double sa0 = alpha * op.a_scale[op.a_row0 + z * op.a_zs_row + ti * TILE + row];
-            const double* sbp = op.b_scale + op.b_row0 + z * op.b_zs_row + tj * TILE + ch * 64;
-            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + ch * 64;
+            const double* sap = op.a_scale + op.a_row0 + z * op.a_zs_row + ti * TILE + q * 32 + r_in;
+            const double* sbp = op.b_scale + op.b_row0 + z * op.b_zs_row + tj * TILE + ch * 64 + cq;
             for (int pass = 0; pass < 2; pass++) {
                 const double beta = pass == 0 ? op.beta : 1.0;
                 // 256^-(lvl+2) of the pass's lowest level: 2^-16 (pass 0), 2^-48 (pass 1)
-                const double sa = sa0 * (pass == 0 ? (1.0 / 65536.0) : (1.0 / 281474976710656.0));
-                // C and the column scales of a 16-column group are fetched before the accumulators are read (for the
-                // first group: before the pass's MMAs have finished), so that their latency is not paid per element
-                double2 old[8], sb2[8];
-                auto prefetch = [&](int cg) {
+                const double ps = alpha * (pass == 0 ? (1.0 / 65536.0) : (1.0 / 281474976710656.0));
+                // step = (row half rh, 32-column group cg): rows q*32 + 16 rh + r_in + {0, 8}, columns 32 cg + 8 j + cq + {0,1}.
+                // C and the scales of a step are fetched one step ahead (for the first step: before the pass's MMAs
+                // have finished), so that their latency is not paid per element
+                double2 old[8], sb2[4];
+                double sA, sB;
+                auto prefetch = [&](int step) {
+                    const int rh = step >> 1, cg = step & 1;
+                    sA = sap[rh * 16] * ps;
+                    sB = sap[rh * 16 + 8] * ps;
+                    const double* crow = C0 + (long long)(rh * 16) * op.ldc + cg * 32;
 #pragma unroll
-                    for (int e = 0; e < 8; e++) {
-                        sb2[e] = *reinterpret_cast<const double2*>(sbp + cg * 16 + 2 * e);
-                        old[e] = (beta != 0.0) ? *reinterpret_cast<const double2*>(Crow + cg * 16 + 2 * e)
-                                               : make_double2(0.0, 0.0);
+                    for (int j = 0; j < 4; j++) {
+                        sb2[j] = *reinterpret_cast<const double2*>(sbp + cg * 32 + 8 * j);
+                        if (beta != 0.0) {
+                            old[2 * j] = *reinterpret_cast<const double2*>(crow + 8 * j);
+                            old[2 * j + 1] = *reinterpret_cast<const double2*>(crow + (long long)8 * op.ldc + 8 * j);
+                        } else {
+                            old[2 * j] = make_double2(0.0, 0.0);
+                            old[2 * j + 1] = make_double2(0.0, 0.0);
+                        }
                     }
                 };
                 prefetch(0);
                 mbar_wait(tmem_full, tphase);
                 tc_fence_after();
+                if (op.prof && blockIdx.x == 0 && z == 0 && item == 0 && threadIdx.x == 64) op.prof[pass * 4 + 2] = clock64();
 #pragma unroll 1
-                for (int cg = 0; cg < 4; cg++) {
+                for (int step = 0; step < 4; step++) {
+                    const int rh = step >> 1, cg = step & 1;
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32 + rh * 16) << 16) + ch * 64 + cg * 32;
                     int v[OZ_L0][16];
                     if (pass == 0) {
 #pragma unroll
-                        for (int a = 0; a < OZ_L0; a++) tmem_ld16(trow + a * OZ_BN + cg * 16, v[a]);
+                        for (int a = 0; a < OZ_L0; a++) tmem_ld_16x256b_x4(taddr + a * OZ_BN, v[a]);
                     } else {
 #pragma unroll
-                        for (int a = 0; a < OZ_S - OZ_L0; a++) tmem_ld16(trow + a * OZ_BN + cg * 16, v[a]);
+                        for (int a = 0; a < OZ_S - OZ_L0; a++) tmem_ld_16x256b_x4(taddr + a * OZ_BN, v[a]);
 #pragma unroll
                         for (int e = 0; e < 16; e++) v[OZ_L0 - 1][e] = 0;
                     }
                     tmem_ld_wait();
                     double2 o[8];
 #pragma unroll
-                    for (int e = 0; e < 8; e++) {
-                        double s0 = (double)v[OZ_L0 - 1][2 * e], s1 = (double)v[OZ_L0 - 1][2 * e + 1];
+                    for (int j = 0; j < 4; j++) {
 #pragma unroll
-                        for (int a = OZ_L0 - 2; a >= 0; a--) {
-                            s0 = fma(s0, 1.0 / 256.0, (double)v[a][2 * e]);
-                            s1 = fma(s1, 1.0 / 256.0, (double)v[a][2 * e + 1]);
+                        for (int h = 0; h < 2; h++) {   // h = 0: row r_in, h = 1: row r_in + 8
+                            double s0 = (double)v[OZ_L0 - 1][4 * j + 2 * h], s1 = (double)v[OZ_L0 - 1][4 * j + 2 * h + 1];
+#pragma unroll
+                            for (int a = OZ_L0 - 2; a >= 0; a--) {
+                                s0 = fma(s0, 1.0 / 256.0, (double)v[a][4 * j + 2 * h]);
+                                s1 = fma(s1, 1.0 / 256.0, (double)v[a][4 * j + 2 * h + 1]);
+                            }
+                            const double sr = h == 0 ? sA : sB;
+                            o[2 * j + h].x = fma(beta, old[2 * j + h].x, s0 * sr * sb2[j].x);
+                            o[2 * j + h].y = fma(beta, old[2 * j + h].y, s1 * sr * sb2[j].y);
                         }
-                        o[e].x = fma(beta, old[e].x, s0 * sa * sb2[e].x);
-                        o[e].y = fma(beta, old[e].y, s1 * sa * sb2[e].y);
                     }
-                    double* dst = Crow + cg * 16;
+                    double* crow = C0 + (long long)(rh * 16) * op.ldc + cg * 32;
+                    if (step + 1 < 4) prefetch(step + 1);
 #pragma unroll
-                    for (int e = 0; e < 8; e++) *reinterpret_cast<double2*>(dst + 2 * e) = o[e];
-                    if (cg + 1 < 4) prefetch(cg + 1);
+                    for (int j = 0; j < 4; j++) {
+                        *reinterpret_cast<double2*>(crow + 8 * j) = o[2 * j];
+                        *reinterpret_cast<double2*>(crow + (long long)8 * op.ldc + 8 * j) = o[2 * j + 1];
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tmem_empty);
+                if (op.prof && blockIdx.x == 0 && z == 0 && item == 0 && threadIdx.x == 64) op.prof[pass * 4 + 3] = clock64();
                 tphase ^= 1;
             }
         }

@@ -1,8 +1,7 @@
 #!/bin/bash
 # schedule experiments of the INT8-sliced factorisation (one bench line each)
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_headline_gpu.py -m gpu -q -x > gpurun_out/oz3_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/oz3_pytest.log
-B="python bench.py --steps 4 --warmup 2 --no-extras --no-cpu-baseline --no-prior-sweep"
+B="python bench.py --steps 4 --warmup 2 --no-extras --no-cpu-baseline --no-prior-sweep --no-dmma-arm"
 run() {
   name=$1; shift
   env "$@" timeout 300 $B > gpurun_out/oz3_$name.log 2>&1
@@ -14,11 +13,7 @@ for l in sys.stdin:
 }
 run default X=1
 run noverlap GPP_OVERLAP_INV=0
+run ipc2 GPP_OZ_IPC=2
 run panel8 GPP_PANEL=8
 run panel16 GPP_PANEL=16
-run ipc2 GPP_OZ_IPC=2
-run trail24 GPP_OZ_MIN_TRAIL=24
-run level2 GPP_OZ_MIN_LEVEL=2
-run level8 GPP_OZ_MIN_LEVEL=8
-run inner0 GPP_OZ_INNER=0
-run inner8 GPP_OZ_INNER=8
+run panel20 GPP_PANEL=20

@@ -375,6 +375,21 @@ static void perf(int n, int kblocks, int tri, int reps) {
     else { op.klo_c = 0; op.khi_c = kblocks; op.alpha = -1.0; op.beta = 1.0; }
     CHECK(launch_oz_gemm(tmA, tmB, op, 1, 0));
     CHECK(cudaDeviceSynchronize());
+    {
+        long long* dprof;
+        CHECK(cudaMalloc(&dprof, 8 * sizeof(long long)));
+        CHECK(cudaMemset(dprof, 0, 8 * sizeof(long long)));
+        OzGemmOp o2 = op;
+        o2.prof = dprof;
+        CHECK(launch_oz_gemm(tmA, tmB, o2, 1, 0));
+        CHECK(cudaDeviceSynchronize());
+        long long hp[8];
+        CHECK(cudaMemcpy(hp, dprof, sizeof(hp), cudaMemcpyDeviceToHost));
+        printf("   CTA 0, first tile (cycles since pass-0 start): p0 issued %lld  complete %lld  epilogue done %lld | p1 start %lld issued %lld"
+               " complete %lld epilogue done %lld\n", hp[1] - hp[0], hp[2] - hp[0], hp[3] - hp[0], hp[4] - hp[0], hp[5] - hp[0],
+               hp[6] - hp[0], hp[7] - hp[0]);
+        cudaFree(dprof);
+    }
     cudaEventRecord(e0);
     for (int i = 0; i < reps; i++) CHECK(launch_oz_gemm(tmA, tmB, op, 1, 0));
     cudaEventRecord(e1);
