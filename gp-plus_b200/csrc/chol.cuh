@@ -18,6 +18,9 @@
 //      only needs the leading tile columns of L starts behind the factorisation on a third stream.
 //   3. lauum: K^-1 = M^T M, one launch over the lower tiles (the upper triangle is not stored on the hot path).
 #pragma once
+#include <stdio.h>
+#include <stdlib.h>
+
 #include <vector>
 
 #include "dgemm_dmma.cuh"
@@ -556,31 +559,55 @@ struct CholLookahead {
     cudaStream_t inv = nullptr;   // lowest priority: early part of the triangular inverse, fills idle SMs
     cudaEvent_t fork = nullptr, join = nullptr, inv_done = nullptr;
     bool inv_pending = false;
-    std::vector<cudaEvent_t> ev_pf, ev_tu;
+    std::vector<cudaEvent_t> ev_pf, ev_tu, ev_m1, ev_s1;
     int panels = 0;
 
+    bool timeline = false;   // GPP_TIMELINE=1 (development): timing-enabled panel events, dumped by dump_timeline()
     cudaError_t init(int T) {
+        timeline = getenv("GPP_TIMELINE") != nullptr && atoi(getenv("GPP_TIMELINE")) != 0;
+        const unsigned evf = timeline ? cudaEventDefault : cudaEventDisableTiming;
         int lo = 0, hi = 0;
         GPP_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         GPP_TRY(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, hi));
         GPP_TRY(cudaStreamCreateWithPriority(&inv, cudaStreamNonBlocking, lo));
-        GPP_TRY(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+        GPP_TRY(cudaEventCreateWithFlags(&fork, evf));
         GPP_TRY(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
         GPP_TRY(cudaEventCreateWithFlags(&inv_done, cudaEventDisableTiming));
         panels = (T + PANEL_BLOCKS - 1) / PANEL_BLOCKS;
         ev_pf.resize(panels);
         ev_tu.resize(panels);
+        ev_m1.resize(panels);
+        ev_s1.resize(panels);
         for (int i = 0; i < panels; i++) {
-            GPP_TRY(cudaEventCreateWithFlags(&ev_pf[i], cudaEventDisableTiming));
-            GPP_TRY(cudaEventCreateWithFlags(&ev_tu[i], cudaEventDisableTiming));
+            GPP_TRY(cudaEventCreateWithFlags(&ev_pf[i], evf));
+            GPP_TRY(cudaEventCreateWithFlags(&ev_tu[i], evf));
+            GPP_TRY(cudaEventCreateWithFlags(&ev_m1[i], evf));
+            GPP_TRY(cudaEventCreateWithFlags(&ev_s1[i], evf));
         }
         return cudaSuccess;
+    }
+    // ms since the fork of the last factorisation at which each panel event completed (call after a synchronise)
+    void dump_timeline(int np) const {
+        if (!timeline) return;
+        for (int p = 0; p < np && p < panels; p++) {
+            float a = -1.f, b = -1.f, c = -1.f, d = -1.f;
+            if (cudaEventElapsedTime(&a, fork, ev_pf[p]) != cudaSuccess) a = -1.f;
+            if (cudaEventElapsedTime(&b, fork, ev_s1[p]) != cudaSuccess) b = -1.f;
+            if (cudaEventElapsedTime(&c, fork, ev_m1[p]) != cudaSuccess) c = -1.f;
+            if (cudaEventElapsedTime(&d, fork, ev_tu[p]) != cudaSuccess) d = -1.f;
+            fprintf(stderr, "[timeline] panel %2d: block/panel factored %7.3f  s1 %7.3f  m1 %7.3f  m2 %7.3f ms\n", p, a, b, c, d);
+        }
+        cudaGetLastError();
     }
     void destroy() {
         for (auto e : ev_pf) cudaEventDestroy(e);
         for (auto e : ev_tu) cudaEventDestroy(e);
+        for (auto e : ev_m1) cudaEventDestroy(e);
+        for (auto e : ev_s1) cudaEventDestroy(e);
         ev_pf.clear();
         ev_tu.clear();
+        ev_m1.clear();
+        ev_s1.clear();
         if (fork) cudaEventDestroy(fork);
         if (join) cudaEventDestroy(join);
         if (inv_done) cudaEventDestroy(inv_done);
@@ -760,6 +787,8 @@ inline cudaError_t potrf_lookahead(double* A, double* M, int ld, int T, double* 
     return cudaSuccess;
 }
 
+// defined below
+inline cudaError_t trtri_doubling(const double* L, double* M, double* X, int ld, int T, cudaStream_t st, OzCtx* oz = nullptr);
 // M (diagonal 128-blocks already hold L_kk^-1) <- L^-1 (lower); X is an N x N scratch.
 // One level of the recursive doubling on the groups [g_lo, g_hi) of 2*hb tiles each:
 //   X21 = L21 * M11 (part & 1), then M21 = -M22 * X21 (part & 2); groups are independent (batched launch).
@@ -826,7 +855,7 @@ inline cudaError_t trtri_level(const double* L, double* M, double* X, int ld, in
 }
 
 inline cudaError_t trtri_doubling(const double* L, double* M, double* X, int ld, int T, cudaStream_t st,
-                                  OzCtx* oz = nullptr) {
+                                  OzCtx* oz) {
     for (int hb = 1; hb < T; hb *= 2)
         GPP_TRY(trtri_level(L, M, X, ld, T, hb, 0, (T + 2 * hb - 1) / (2 * hb), 3, st, 0, oz));
     return cudaSuccess;
@@ -856,6 +885,99 @@ inline cudaError_t trtri_late(const double* L, double* M, double* X, int ld, int
     for (int hb = 1; hb < H; hb *= 2)
         GPP_TRY(trtri_level(L, M, X, ld, T, hb, H / (2 * hb), (T + 2 * hb - 1) / (2 * hb), 3, st, 0, oz));
     return trtri_level(L, M, X, ld, T, H, 0, 1, 2, st, 0, oz);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Lazy-panel variant for the INT8-sliced path.  With the trailing updates ~3x faster than on DMMA, the panel chain of
+// potrf_lookahead (leaf / TRSM / in-panel updates over ALL rows below: ~2.3 ms per 1536-column panel) became the
+// critical path.  Here the chain only factors the DIAGONAL block of a panel (12 x 12 tiles) and inverts it
+// (W = L_pp^-1, recursive doubling inside the block -- these are final entries of L^-1); the rows below are then
+// solved in one integer GEMM, L[rows, panel] = A[rows, panel] W^T, which is throughput work:
+//
+//   side:  B(0) s1(0) u1(0) B(1) [wait m1(0)] s1(1) [wait m2(0)] u1(1) B(2) ...
+//   main:       [wait B(0)] s2(0) [wait s1(0)] m1(0) m2(0) m3(0)   [wait B(1)] s2(1) ...
+//
+//   B(p)   factor + invert the diagonal block of panel p, cut W into digit planes
+//   s1(p)  solve the rows of the NEXT diagonal block (tile rows [pend, nend)), cut them into planes
+//   u1(p)  update of block (p+1, p+1) with panel p                     -> B(p+1) can start
+//   s2(p)  solve the remaining rows [nend, T), cut them into planes
+//   m1(p)  update of tile-column block p+1, rows >= nend               -> s1(p+1) can start
+//   m2(p)  update of tile-column block p+2, rows >= nend               -> u1(p+1) can start
+//   m2b(p) update of tile-column block p+3
+//   m3(p)  update of everything to the right of block p+3, issued after the urgent pieces of panel p+1
+inline cudaError_t potrf_lazy(double* A, double* M, int ld, int T, double* logdet_part, int* info, cudaStream_t st,
+                              CholLookahead& la, double* X, OzCtx& oz) {
+    const int PB = OzCtx::LAZY_PB;
+    const int NP = (T + PB - 1) / PB;
+    if (NP > la.panels) return cudaErrorInvalidValue;
+    const int H = trtri_split_point(T);
+    const bool overlap = g_overlap_inverse && X != nullptr && H > 0 && NP > 1;
+    la.inv_pending = false;
+    GPP_TRY(cudaEventRecord(la.fork, st));
+    GPP_TRY(cudaStreamWaitEvent(la.side, la.fork, 0));
+    int def_p0 = -1, def_pend = 0, def_c0 = 0, def_slot = 0;   // deferred bulk update
+    for (int p = 0; p < NP; p++) {
+        const int p0 = p * PB;
+        const int pend = (p0 + PB < T) ? p0 + PB : T;
+        const int nend = (pend + PB < T) ? pend + PB : T;
+        const int n2end = (nend + PB < T) ? nend + PB : T;
+        const int buf = p & 1, slot = p & 3;
+        // ---- B(p): diagonal block on the chain (row limit = pend) ----
+        GPP_TRY(panel_factor(A, M, ld, pend, p0, pend, logdet_part, info, la.side, nullptr));
+        if (pend < T) {
+            const long long o = (long long)p0 * TILE * ld + (long long)p0 * TILE;
+            GPP_TRY(trtri_doubling(A + o, M + o, X + o, ld, pend - p0, la.side, nullptr));
+            GPP_TRY(oz_split_w(oz, M + o, ld, pend - p0, buf, la.side));
+        }
+        GPP_TRY(cudaEventRecord(la.ev_pf[p], la.side));
+        if (pend >= T) break;
+        // ---- side: the pieces the next diagonal block waits for ----
+        if (p >= 1) GPP_TRY(cudaStreamWaitEvent(la.side, la.ev_m1[p - 1], 0));
+        GPP_TRY(oz_panel_solve(oz, A, ld, p0, pend, pend, nend, buf, 4, la.side));                 // s1
+        GPP_TRY(oz_split_panel_rows(oz, A, ld, p0, pend, pend, nend, slot, la.side));
+        GPP_TRY(cudaEventRecord(la.ev_s1[p], la.side));
+        if (p >= 1) GPP_TRY(cudaStreamWaitEvent(la.side, la.ev_tu[p - 1], 0));
+        GPP_TRY(oz_update_region(oz, A, ld, p0, pend, pend, nend, pend, nend, slot, la.side));      // u1
+        // ---- main: throughput work; the bulk update m3 of a panel is issued one panel late, behind the next
+        // panel's urgent pieces, so that the chain never queues behind it ----
+        GPP_TRY(cudaStreamWaitEvent(st, la.ev_pf[p], 0));
+        const int n3end = (n2end + PB < T) ? n2end + PB : T;
+        if (nend < T) {
+            GPP_TRY(oz_panel_solve(oz, A, ld, p0, pend, nend, T, buf, 5, st, true));                // s2
+            GPP_TRY(oz_split_panel_rows(oz, A, ld, p0, pend, nend, T, slot, st));
+            GPP_TRY(cudaStreamWaitEvent(st, la.ev_s1[p], 0));
+            GPP_TRY(oz_update_region(oz, A, ld, p0, pend, nend, T, pend, nend, slot, st, true));    // m1
+            GPP_TRY(cudaEventRecord(la.ev_m1[p], st));
+            if (overlap && !la.inv_pending && pend >= H) {
+                // every row of the first H tile columns of L is final: their share of L^-1 runs behind the rest
+                GPP_TRY(cudaStreamWaitEvent(la.inv, la.ev_m1[p], 0));
+                GPP_TRY(trtri_early(A, M, X, ld, T, la.inv, &oz));
+                GPP_TRY(cudaEventRecord(la.inv_done, la.inv));
+                la.inv_pending = true;
+            }
+            GPP_TRY(oz_update_region(oz, A, ld, p0, pend, nend, T, nend, n2end, slot, st, true));   // m2
+            GPP_TRY(cudaEventRecord(la.ev_tu[p], st));
+            if (n2end < T) GPP_TRY(oz_update_region(oz, A, ld, p0, pend, n2end, T, n2end, n3end, slot, st, true));  // m2b
+        } else {
+            GPP_TRY(cudaEventRecord(la.ev_m1[p], st));
+            GPP_TRY(cudaEventRecord(la.ev_tu[p], st));
+        }
+        if (def_p0 >= 0) {   // m3 of the previous panel
+            GPP_TRY(oz_update_region(oz, A, ld, def_p0, def_pend, def_c0, T, def_c0, T, def_slot, st, true));
+            def_p0 = -1;
+        }
+        if (n3end < T) {
+            def_p0 = p0;
+            def_pend = pend;
+            def_c0 = n3end;
+            def_slot = slot;
+        }
+    }
+    if (def_p0 >= 0) GPP_TRY(oz_update_region(oz, A, ld, def_p0, def_pend, def_c0, T, def_c0, T, def_slot, st, true));
+    GPP_TRY(cudaEventRecord(la.join, la.side));
+    GPP_TRY(cudaStreamWaitEvent(st, la.join, 0));
+    return cudaSuccess;
 }
 
 // Kinv = M^T M over the lower tiles; M lower: k-blocks [ti, T).  The hot path reads lower tiles only (the gradient

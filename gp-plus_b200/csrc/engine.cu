@@ -410,6 +410,8 @@ extern "C" int gpp_create(const gpp_problem* p, int device, gpp_handle** out) {
             if ((e = getenv("GPP_OZ_IPC")) != nullptr) g_oz_items_per_cta = atoi(e) > 0 ? atoi(e) : 2;
             if ((e = getenv("GPP_OZ_NEXT")) != nullptr) h->oz->next_on_oz = atoi(e);
             if ((e = getenv("GPP_OZ_INNER")) != nullptr) h->oz->inner_min_k = atoi(e);
+            if ((e = getenv("GPP_OZ_LAZY")) != nullptr) h->oz->lazy = atoi(e);
+            if ((e = getenv("GPP_OZ_STAGGER")) != nullptr) h->oz->stagger = atoi(e);
             CKH(h->oz->init((int)h->np));
         }
     }
@@ -594,7 +596,9 @@ static int stage_factor(gpp_handle* h) {
         CK(launch_cov(ca, h->kernel, h->st));
     }
     mark(h, EV_COV);
-    if (h->use_lookahead)
+    if (h->use_lookahead && h->oz && h->oz->ready && h->oz->lazy && h->T >= 3 * OzCtx::LAZY_PB)
+        CK(potrf_lazy(h->A, h->M, (int)h->np, h->T, h->logdet_part, h->info, h->st, h->la, h->S, *h->oz));
+    else if (h->use_lookahead)
         CK(potrf_lookahead(h->A, h->M, (int)h->np, h->T, h->logdet_part, h->info, h->st, h->la, h->S, h->oz));
     else
         CK(potrf_blocked(h->A, h->M, (int)h->np, h->T, h->logdet_part, h->info, h->st));
@@ -792,6 +796,7 @@ static int run_eval(gpp_handle* h, const gpp_hyper* hy, int want_grad, int first
             if (rc != GPP_OK) return rc;
             mark(h, EV_END);
             CK(cudaStreamSynchronize(h->st));
+            if (h->la.timeline) h->la.dump_timeline((h->T + OzCtx::LAZY_PB - 1) / OzCtx::LAZY_PB);
             info = failed ? failed : (int)h->res_host[2];
         } else {
             int rc = enqueue_eval(h, want_grad);

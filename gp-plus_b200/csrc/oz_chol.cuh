@@ -18,7 +18,16 @@ struct OzCtx {
     bool ready = false;
     int np = 0, T = 0;
     OzPlanes PP, PA, PB;
-    double* pscale[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // [4]: in-panel updates (side stream only)
+    // [0..3]: factored panels by panel index mod 4; [4]: side-stream scratch (in-panel updates, panel rows before their
+    // solve); [5]: main-stream scratch (panel rows before their solve)
+    double* pscale[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // lazy panels: only the diagonal block of a panel is factored on the latency-bound chain; the rows below are solved
+    // against its explicit inverse W = L_pp^-1 by one integer GEMM.  W's digit planes, double-buffered by panel parity:
+    static constexpr int LAZY_PB = 12;     // panel width in 128-tiles
+    int lazy = 1;
+    int stagger = 6000;            // ns per 128-block of K: estimated duration of one 128x128 item, see OzGemmOp.stagger_ns
+    OzPlanes PW[2];
+    CUtensorMap mPW_b[2];
     int next_on_oz = 1;            // U(p,p+1), the update of the next panel's own columns, also runs here
     int inner_min_k = 4;           // in-panel (recursive) updates with K >= this many tiles run here; 0 = never
     CUtensorMap mPP_a, mPP_b, mPA_a, mPB_a, mPB_b;
@@ -55,8 +64,13 @@ struct OzCtx {
         if ((e = alloc_planes(PP, np, bytes)) != cudaSuccess) return e;
         if ((e = alloc_planes(PA, np, bytes)) != cudaSuccess) return e;
         if ((e = alloc_planes(PB, np, bytes)) != cudaSuccess) return e;
-        for (int i = 0; i < 5; i++)
+        for (int i = 0; i < 6; i++)
             if ((e = cudaMalloc(&pscale[i], sizeof(double) * np)) != cudaSuccess) return e;
+        for (int i = 0; i < 2; i++) {
+            const long long wr = (long long)LAZY_PB * TILE;
+            if ((e = alloc_planes(PW[i], wr, bytes)) != cudaSuccess) return e;
+            if ((e = oz_make_map(&mPW_b[i], PW[i].planes, wr, (long long)OZ_S * wr, wr, OZ_BN)) != cudaSuccess) return e;
+        }
         const long long rows = (long long)OZ_S * np;
         if ((e = oz_make_map(&mPP_a, PP.planes, np, rows, np, OZ_BM)) != cudaSuccess) return e;
         if ((e = oz_make_map(&mPP_b, PP.planes, np, rows, np, OZ_BN)) != cudaSuccess) return e;
@@ -70,10 +84,12 @@ struct OzCtx {
         free_planes(PP);
         free_planes(PA);
         free_planes(PB);
-        for (int i = 0; i < 5; i++) {
+        for (int i = 0; i < 6; i++) {
             if (pscale[i]) cudaFree(pscale[i]);
             pscale[i] = nullptr;
         }
+        free_planes(PW[0]);
+        free_planes(PW[1]);
         ready = false;
     }
 };
@@ -116,7 +132,85 @@ inline cudaError_t oz_trailing_update(OzCtx& oz, double* A, int ld, int T, int p
         op.lower_filter = 1;
         op.lower_off = 0;
     }
+    op.stagger_ns = oz.stagger * (pend - p0);
     return launch_oz_gemm(oz.mPP_a, oz.mPP_b, op, 1, st);
+}
+
+// general form: C[i,j] -= sum_{k in [p0,pend)} L[i,k] L[j,k] for tile rows i in [r0, r1), tile columns j in [c0, c1), i >= j
+// (r0 >= c0; digit planes and scales of panel slot `slot` must cover rows [c0, c1) and [r0, r1))
+inline cudaError_t oz_update_region(OzCtx& oz, double* A, int ld, int p0, int pend, int r0, int r1, int c0, int c1, int slot,
+                                    cudaStream_t st, bool stagger = false) {
+    if (c1 <= c0 || r1 <= r0) return cudaSuccess;
+    OzGemmOp op = oz_default();
+    op.a_plane_rows = op.b_plane_rows = oz.np;
+    op.a_row0 = r0 * TILE;
+    op.b_row0 = c0 * TILE;
+    op.a_k0 = op.b_k0 = p0 * TILE;
+    op.a_scale = op.b_scale = oz.pscale[slot];
+    op.C = A + (long long)r0 * TILE * ld + (long long)c0 * TILE;
+    op.ldc = ld;
+    op.tiles_m = op.tiles_m_last = r1 - r0;
+    op.tiles_n = c1 - c0;
+    op.klo_c = 0;
+    op.khi_c = pend - p0;
+    op.alpha = -1.0;
+    op.beta = 1.0;
+    if (r0 == c0 && r1 - r0 == c1 - c0) {
+        op.map = MAP_TRI;
+    } else {
+        op.lower_filter = 1;
+        op.lower_off = r0 - c0;
+    }
+    if (stagger) op.stagger_ns = oz.stagger * (pend - p0);
+    return launch_oz_gemm(oz.mPP_a, oz.mPP_b, op, 1, st);
+}
+
+// digit planes of W = L_pp^-1 (lower triangular pw x pw tiles, given in M's diagonal block) into PW[buf]
+inline cudaError_t oz_split_w(OzCtx& oz, const double* Wblk, int ld, int pw, int buf, cudaStream_t st) {
+    return oz_split_rows(Wblk, ld, 0, pw * TILE, pw * TILE, pw * TILE, oz.PW[buf], 0, 0, 0, 0, 1, st);
+}
+
+// panel rows [r0, r1) x tile columns [p0, pend):  X = A W^T in place (X[i,c] = sum_{k <= c} A[i,k] W[c,k]); the rows are
+// cut into digit planes first (scratch scale slot `pre_slot`), so writing the result over A is safe
+inline cudaError_t oz_panel_solve(OzCtx& oz, double* A, int ld, int p0, int pend, int r0, int r1, int buf, int pre_slot,
+                                  cudaStream_t st, bool stagger = false) {
+    if (r1 <= r0) return cudaSuccess;
+    OzPlanes pp = oz.PP;
+    pp.scale = oz.pscale[pre_slot];
+    const int rows = (r1 - r0) * TILE;
+    cudaError_t e = oz_split_rows(A + (long long)r0 * TILE * ld + (long long)p0 * TILE, ld, 0, rows, rows, (pend - p0) * TILE,
+                                  pp, (long long)r0 * TILE, (long long)p0 * TILE, 0, 0, 1, st);
+    if (e != cudaSuccess) return e;
+    OzGemmOp op = oz_default();
+    op.a_plane_rows = oz.np;
+    op.b_plane_rows = OzCtx::LAZY_PB * TILE;
+    op.a_row0 = r0 * TILE;
+    op.a_k0 = p0 * TILE;
+    op.b_row0 = 0;
+    op.b_k0 = 0;
+    op.a_scale = oz.pscale[pre_slot];
+    op.b_scale = oz.PW[buf].scale;
+    op.C = A + (long long)r0 * TILE * ld + (long long)p0 * TILE;
+    op.ldc = ld;
+    op.tiles_m = op.tiles_m_last = r1 - r0;
+    op.tiles_n = pend - p0;
+    op.klo_sel = KSEL_CONST;
+    op.klo_c = 0;
+    op.khi_sel = KSEL_TJ;
+    op.khi_c = 1;
+    if (stagger) op.stagger_ns = oz.stagger * (pend - p0) / 2;
+    return launch_oz_gemm(oz.mPP_a, oz.mPW_b[buf], op, 1, st);
+}
+
+// digit planes of solved panel rows [r0, r1) (operand of the trailing updates), scale slot `slot`
+inline cudaError_t oz_split_panel_rows(OzCtx& oz, const double* A, int ld, int p0, int pend, int r0, int r1, int slot,
+                                       cudaStream_t st) {
+    if (r1 <= r0) return cudaSuccess;
+    OzPlanes pp = oz.PP;
+    pp.scale = oz.pscale[slot];
+    const int rows = (r1 - r0) * TILE;
+    return oz_split_rows(A + (long long)r0 * TILE * ld + (long long)p0 * TILE, ld, 0, rows, rows, (pend - p0) * TILE, pp,
+                         (long long)r0 * TILE, (long long)p0 * TILE, 0, 0, 1, st);
 }
 
 inline bool oz_use_level(const OzCtx* oz, int hb) { return oz && oz->ready && hb >= oz->min_level_tiles && hb <= 128; }

@@ -73,6 +73,9 @@ struct OzGemmOp {
     int klo_sel, klo_c, khi_sel, khi_c;
     double alpha, beta;
     int n_tiles;                     // 128x128 tiles per batch entry (set by launch_oz_gemm)
+    int stagger_ns;                  // > 0: CTA b of the first wave starts (b mod 148) / 148 of this many ns late, so that
+                                     // CTAs (equal work each) retire evenly spread in time instead of in synchronised
+                                     // waves and a higher-priority stream finds a free SM within microseconds
     long long* prof;                 // optional (development): clock64 stamps of CTA 0's first item, 4 per pass:
                                      // accumulators free, MMAs issued, accumulators complete, epilogue done
 };
@@ -200,6 +203,10 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int z = blockIdx.y;
     const int tm = (z == (int)gridDim.y - 1) ? op.tiles_m_last : op.tiles_m;
     const int n_items = op.n_tiles;
+    if (op.stagger_ns > 0 && blockIdx.x < GEMM_NUM_SMS) {
+        for (int w = (int)((long long)blockIdx.x * op.stagger_ns / GEMM_NUM_SMS); w > 0; w -= 1000)
+            __nanosleep(w > 1000 ? 1000 : w);
+    }
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
