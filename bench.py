@@ -340,7 +340,7 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel -------------------------------------------------------------------------
     # The three O(N^3) stages (factorisation trailing updates, L^-1, K^-1) run either on the INT8-sliced tcgen05 GEMM
-    # (oz_gemm_kernel; default from N = 4096) or on the FP64 DMMA GEMM (dgemm_dmma_kernel; GPP_FP64=dmma).
+    # (oz_gemm_kernel; default from N = 3072) or on the FP64 DMMA GEMM (dgemm_dmma_kernel; GPP_FP64=dmma).
     fp64_mode = eng.fp64_mode()
     peak = measure_fp64_peak(local)
     n3 = float(n) ** 3

@@ -395,10 +395,11 @@ extern "C" int gpp_create(const gpp_problem* p, int device, gpp_handle** out) {
     }
     CKH(h->la.init(h->T));
     {
-        // FP64 work of the O(N^3) stages: exact integer GEMMs on the INT8 tcgen05 tensor cores from Np = 4096 up
-        // (below that the stages are latency-bound and the DMMA kernels win); GPP_FP64=dmma keeps everything on DMMA
+        // FP64 work of the O(N^3) stages: exact integer GEMMs on the INT8 tcgen05 tensor cores from Np = 3072 up
+        // (measured: 3.08 vs 3.42 ms at N = 3072, 14.8 vs 22.0 at 8192, 28.8 vs 63.5 at 12288; below that an evaluation
+        // is a CUDA-graph replay of latency-bound launches); GPP_FP64=dmma keeps everything on DMMA
         const char* e = getenv("GPP_FP64");
-        bool int8 = h->T >= 32;
+        bool int8 = h->T >= 24;
         const int mode = g_fp64_mode.load();
         if (mode == GPP_FP64_DMMA) int8 = false;
         if (mode == GPP_FP64_INT8) int8 = h->T >= 8;   // forced: the stages still pick DMMA for shapes that are too small

@@ -235,7 +235,7 @@ int gpp_objective_collect(gpp_handle* h, double* value, double* grad, gpp_mll_re
  * FP64 results within the parity tolerances (objective 1e-9, gradient 1e-8; observed 2e-13 / 3e-13 at N = 16384):
  *   GPP_FP64_DMMA  mma.sync FP64 tensor-core tiles (IEEE FP64 products and sums)
  *   GPP_FP64_INT8  operands cut into 7 signed base-256 digit planes per power-of-two-scaled row, exact integer products
- *                  on the INT8 tcgen05 tensor cores, FP64 recombination (csrc/oz_gemm.cuh).  Default from N = 4096.
+ *                  on the INT8 tcgen05 tensor cores, FP64 recombination (csrc/oz_gemm.cuh).  Default from N = 3072.
  * gpp_set_fp64_mode sets the process-wide choice for handles created afterwards (-1 = by size, the default;
  * the environment variable GPP_FP64=dmma has the same effect as 0) and returns the previous one;
  * gpp_get_fp64_mode reports what a handle uses. */

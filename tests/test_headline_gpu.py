@@ -5,7 +5,7 @@
 * engine at N=16384 vs the committed oracle output tests/golden/c4_n16384_matern52.json (generated once by
   ``python tests/golden/make_golden.py --c4 16384``; bench.py asserts on the same file).
 
-From N = 4096 up the engine's O(N^3) stages run as exact integer GEMMs on the INT8 tcgen05 tensor cores
+From N = 3072 up the engine's O(N^3) stages run as exact integer GEMMs on the INT8 tcgen05 tensor cores
 (csrc/oz_gemm.cuh: 7 digit planes per operand); the tests above therefore exercise that path.  Two more cases pin it:
 the same points with the exact-DMMA arithmetic (gpp_set_fp64_mode(0)), and an ill-conditioned covariance
 (condition ~1e8: noise at its 1e-8 floor, long lengthscales) on both arithmetics.
