@@ -282,9 +282,8 @@ __device__ __forceinline__ void acc_store32(double* dst, int ldd, const double (
 }
 
 // prof (optional): clock64 stamps written by thread 0 / lane 0 of the inverse warp
-__global__ void __launch_bounds__(LEAF_THREADS, 1)
-leaf_potrf_trinv_kernel(double* A, int ld, int kb, double* M, double* logdet_part, int* info, long long* prof) {
-    extern __shared__ __align__(16) double sm[];
+__device__ __forceinline__ void leaf_potrf_trinv_body(double* A, int ld, int kb, double* M, double* logdet_part, int* info,
+                                                      long long* prof, double* sm) {
     double* S = sm;
     double* xd = S + L2_S;
     double* Xd = xd + L2_XD;
@@ -454,13 +453,246 @@ leaf_potrf_trinv_kernel(double* A, int ld, int kb, double* M, double* logdet_par
 #undef GPP_STAMP
 }
 
+__global__ void __launch_bounds__(LEAF_THREADS, 1)
+leaf_potrf_trinv_kernel(double* A, int ld, int kb, double* M, double* logdet_part, int* info, long long* prof) {
+    extern __shared__ __align__(16) double sm[];
+    leaf_potrf_trinv_body(A, ld, kb, M, logdet_part, info, prof, sm);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Diagonal block of a panel (pw x pw tiles, pw <= 16) in ONE launch: a left-looking tile dataflow.  The tiles are
+// numbered column by column; CTA c handles tiles c, c + G, c + 2G, ... in that order.  Tile (i,j), i > j:
+//   P = sum_{k<j} L(i,k) L(j,k)^T (DMMA, operands streamed from L2 as soon as their flags are up),
+//   L(i,j) = (A(i,j) - P) L_jj^-T   via the explicit inverse of the diagonal tile (as the TRSM launches do);
+// tile (j,j): A(j,j) -= sum_{k<j} L(j,k) L(j,k)^T, then the leaf (factor + inverse) in place.
+// A finished tile is published with a release store of the launch's epoch to its flag; consumers spin on an acquire
+// load.  Dependencies only point to lower tile numbers and CTAs are dispatched in index order, so the scheme cannot
+// deadlock even when only some CTAs are resident.  Replaces ~37 dependent launches per 12-tile block
+// (leaf / TRSM / update / recursion updates: ~135 us per 128-column step) by flag hand-offs (~75 us per step).
+constexpr int BLKP_THREADS = 256;
+constexpr int BLKP_NST = 3;
+constexpr int BLKP_XLD = 132;
+constexpr int BLKP_STAGE = TILE * LDS_KC;   // doubles per operand and stage
+constexpr int BLKP_SMEM_TRSM = (TILE * BLKP_XLD + BLKP_NST * BLKP_STAGE) * 8;
+constexpr int BLKP_SMEM_UPD = (2 * BLKP_NST * BLKP_STAGE) * 8;
+constexpr int BLKP_SMEM_BYTES = (LEAF2_SMEM_BYTES > BLKP_SMEM_TRSM ? LEAF2_SMEM_BYTES : BLKP_SMEM_TRSM) > BLKP_SMEM_UPD
+                                    ? (LEAF2_SMEM_BYTES > BLKP_SMEM_TRSM ? LEAF2_SMEM_BYTES : BLKP_SMEM_TRSM)
+                                    : BLKP_SMEM_UPD;
+static_assert(BLKP_SMEM_BYTES <= 232448, "block factorisation shared memory exceeds the 227 KB per-CTA limit");
+static_assert(LEAF_THREADS == BLKP_THREADS, "the leaf body runs inside the block kernel");
+
+__device__ __forceinline__ void blkp_wait(const int* flag, int epoch) {
+    if (threadIdx.x == 0) {
+        int v;
+        unsigned spins = 0;
+        for (;;) {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+            if (v == epoch) break;
+            __nanosleep(100);
+            if (++spins > (1u << 24)) __trap();   // ~2 s: a lost hand-off surfaces as a CUDA error, not a hang
+        }
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void blkp_post(int* flag, int epoch) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+}
+
+// acc += A(128 x 128) B(128 x 128)^T, both operands k-contiguous in global memory (read through L2 by cp.async.cg)
+__device__ __forceinline__ void blkp_mma_gg(double (&acc)[4][8][2], const double* Ag, int lda, const double* Bg, int ldb,
+                                            double* pipe, int tid, int wm0, int wn0, int g, int t) {
+    constexpr int NCH = TILE / BK;
+    double* sA = pipe;
+    double* sB = pipe + BLKP_NST * BLKP_STAGE;
+#pragma unroll
+    for (int s = 0; s < BLKP_NST - 1; s++) {
+        load_chunk<true, TILE, BLKP_THREADS>(sA + s * BLKP_STAGE, Ag + s * BK, lda, tid);
+        load_chunk<true, TILE, BLKP_THREADS>(sB + s * BLKP_STAGE, Bg + s * BK, ldb, tid);
+        cp_async_commit();
+    }
+    for (int c = 0; c < NCH; c++) {
+        cp_async_wait<BLKP_NST - 2>();
+        __syncthreads();
+        const int cn = c + BLKP_NST - 1;
+        if (cn < NCH) {
+            const int s = cn % BLKP_NST;
+            load_chunk<true, TILE, BLKP_THREADS>(sA + s * BLKP_STAGE, Ag + cn * BK, lda, tid);
+            load_chunk<true, TILE, BLKP_THREADS>(sB + s * BLKP_STAGE, Bg + cn * BK, ldb, tid);
+        }
+        cp_async_commit();
+        const double* a_s = sA + (c % BLKP_NST) * BLKP_STAGE;
+        const double* b_s = sB + (c % BLKP_NST) * BLKP_STAGE;
+#pragma unroll
+        for (int kk = 0; kk < BK / 4; kk++) {
+            double af[4], bf[8];
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++) af[mi] = a_s[(wm0 + mi * 8 + g) * LDS_KC + kk * 4 + t];
+#pragma unroll
+            for (int ni = 0; ni < 8; ni++) bf[ni] = b_s[(wn0 + ni * 8 + g) * LDS_KC + kk * 4 + t];
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+                for (int ni = 0; ni < 8; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+}
+
+// acc = Xs(128 x 128, shared memory, leading dimension BLKP_XLD) B(128 x 128)^T, B k-contiguous in global memory
+__device__ __forceinline__ void blkp_mma_sg(double (&acc)[4][8][2], const double* Xs, const double* Bg, int ldb, double* pipe,
+                                            int tid, int wm0, int wn0, int g, int t) {
+    constexpr int NCH = TILE / BK;
+    double* sB = pipe;
+#pragma unroll
+    for (int s = 0; s < BLKP_NST - 1; s++) {
+        load_chunk<true, TILE, BLKP_THREADS>(sB + s * BLKP_STAGE, Bg + s * BK, ldb, tid);
+        cp_async_commit();
+    }
+    for (int c = 0; c < NCH; c++) {
+        cp_async_wait<BLKP_NST - 2>();
+        __syncthreads();
+        const int cn = c + BLKP_NST - 1;
+        if (cn < NCH) load_chunk<true, TILE, BLKP_THREADS>(sB + (cn % BLKP_NST) * BLKP_STAGE, Bg + cn * BK, ldb, tid);
+        cp_async_commit();
+        const double* b_s = sB + (c % BLKP_NST) * BLKP_STAGE;
+#pragma unroll
+        for (int kk = 0; kk < BK / 4; kk++) {
+            double af[4], bf[8];
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++) af[mi] = Xs[(wm0 + mi * 8 + g) * BLKP_XLD + c * BK + kk * 4 + t];
+#pragma unroll
+            for (int ni = 0; ni < 8; ni++) bf[ni] = b_s[(wn0 + ni * 8 + g) * LDS_KC + kk * 4 + t];
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+                for (int ni = 0; ni < 8; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+}
+
+struct BlockPotrfArgs {
+    double* A;            // whole matrix (leading dimension ld)
+    double* M;
+    int ld;
+    int t0, pw;           // first tile and width of the diagonal block
+    double* logdet_part;
+    int* info;
+    int* flags;           // [pw * pw], value == epoch: tile final
+    int epoch;
+};
+
+__global__ void __launch_bounds__(BLKP_THREADS, 1) block_potrf_kernel(const BlockPotrfArgs a) {
+    extern __shared__ __align__(16) double sm[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm0 = (warp >> 1) * 32, wn0 = (warp & 1) * 64;
+    const int pw = a.pw, ld = a.ld;
+    const int ntiles = pw * (pw + 1) / 2;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        // column-major numbering of the lower tiles: column j holds rows j .. pw-1
+        int j = 0, rem = tile;
+        while (rem >= pw - j) { rem -= pw - j; j++; }
+        const int i = j + rem;
+        double* Aij = a.A + (long long)(a.t0 + i) * TILE * ld + (long long)(a.t0 + j) * TILE;
+        double acc[4][8][2];
+#pragma unroll
+        for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+            for (int ni = 0; ni < 8; ni++) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+        for (int k = 0; k < j; k++) {
+            blkp_wait(a.flags + i * pw + k, a.epoch);
+            if (i != j) blkp_wait(a.flags + j * pw + k, a.epoch);
+            const double* Lik = a.A + (long long)(a.t0 + i) * TILE * ld + (long long)(a.t0 + k) * TILE;
+            const double* Ljk = a.A + (long long)(a.t0 + j) * TILE * ld + (long long)(a.t0 + k) * TILE;
+            blkp_mma_gg(acc, Lik, ld, Ljk, ld, sm, tid, wm0, wn0, g, t);
+        }
+        if (i == j) {
+            // updated diagonal tile back to global memory, then factor + invert it in place
+            if (j > 0) {
+#pragma unroll
+                for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+                    for (int ni = 0; ni < 8; ni++) {
+                        double2* p2 = reinterpret_cast<double2*>(Aij + (long long)(wm0 + mi * 8 + g) * ld + wn0 + ni * 8 + 2 * t);
+                        double2 v = *p2;
+                        v.x -= acc[mi][ni][0];
+                        v.y -= acc[mi][ni][1];
+                        *p2 = v;
+                    }
+                __threadfence();
+                __syncthreads();
+            }
+            leaf_potrf_trinv_body(a.A, ld, a.t0 + j, a.M, a.logdet_part, a.info, nullptr, sm);
+            blkp_post(a.flags + j * pw + j, a.epoch);
+        } else {
+            // X = A(i,j) - P into shared memory, then L(i,j) = X L_jj^-T
+            double* Xs = sm;
+            double* pipe = sm + TILE * BLKP_XLD;
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+                for (int ni = 0; ni < 8; ni++) {
+                    const int r = wm0 + mi * 8 + g, c = wn0 + ni * 8 + 2 * t;
+                    double2 v = *reinterpret_cast<const double2*>(Aij + (long long)r * ld + c);
+                    v.x -= acc[mi][ni][0];
+                    v.y -= acc[mi][ni][1];
+                    *reinterpret_cast<double2*>(Xs + r * BLKP_XLD + c) = v;
+                    acc[mi][ni][0] = 0.0;
+                    acc[mi][ni][1] = 0.0;
+                }
+            blkp_wait(a.flags + j * pw + j, a.epoch);   // L_jj^-1 is in M (also orders the Xs stores before the reads)
+            const double* Winv = a.M + (long long)(a.t0 + j) * TILE * ld + (long long)(a.t0 + j) * TILE;
+            blkp_mma_sg(acc, Xs, Winv, ld, pipe, tid, wm0, wn0, g, t);
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+                for (int ni = 0; ni < 8; ni++) {
+                    double2 v;
+                    v.x = acc[mi][ni][0];
+                    v.y = acc[mi][ni][1];
+                    *reinterpret_cast<double2*>(Aij + (long long)(wm0 + mi * 8 + g) * ld + wn0 + ni * 8 + 2 * t) = v;
+                }
+            blkp_post(a.flags + i * pw + j, a.epoch);
+        }
+        __syncthreads();   // shared memory is re-carved by the next tile
+    }
+}
+
 inline cudaError_t chol_set_attributes() {
     cudaError_t e = cudaFuncSetAttribute(leaf_potrf_trinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          LEAF2_SMEM_BYTES);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(block_potrf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BLKP_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
     e = oz_set_attributes();
     if (e != cudaSuccess) return e;
     return gemm_set_attributes();
+}
+
+// diagonal block [t0, t0 + pw) of A in one launch (flags: pw * pw ints owned by the caller; epoch must differ from every
+// value left in them, e.g. a per-handle launch counter)
+inline cudaError_t launch_block_potrf(double* A, double* M, int ld, int t0, int pw, double* logdet_part, int* info, int* flags,
+                                      int epoch, int ctas, cudaStream_t st) {
+    BlockPotrfArgs a;
+    a.A = A;
+    a.M = M;
+    a.ld = ld;
+    a.t0 = t0;
+    a.pw = pw;
+    a.logdet_part = logdet_part;
+    a.info = info;
+    a.flags = flags;
+    a.epoch = epoch;
+    const int ntiles = pw * (pw + 1) / 2;
+    const int gx = ctas < ntiles ? ctas : ntiles;
+    block_potrf_kernel<<<gx, BLKP_THREADS, BLKP_SMEM_BYTES, st>>>(a);
+    count_launch();
+    return cudaGetLastError();
 }
 
 inline cudaError_t launch_leaf(double* A, int ld, int col, double* M, double* logdet_part, int* info, cudaStream_t st,
@@ -562,6 +794,9 @@ struct CholLookahead {
     std::vector<cudaEvent_t> ev_pf, ev_tu, ev_m1, ev_s1;
     int panels = 0;
 
+    int* blk_flags = nullptr;   // tile flags of block_potrf_kernel (256 ints), epoch = launch counter
+    int blk_epoch = 0;
+    int blk_ctas = 24;          // CTAs of one diagonal-block launch (GPP_BLOCK_CTAS; 0 = the launch-per-step chain)
     bool timeline = false;   // GPP_TIMELINE=1 (development): timing-enabled panel events, dumped by dump_timeline()
     cudaError_t init(int T) {
         timeline = getenv("GPP_TIMELINE") != nullptr && atoi(getenv("GPP_TIMELINE")) != 0;
@@ -573,6 +808,9 @@ struct CholLookahead {
         GPP_TRY(cudaEventCreateWithFlags(&fork, evf));
         GPP_TRY(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
         GPP_TRY(cudaEventCreateWithFlags(&inv_done, cudaEventDisableTiming));
+        GPP_TRY(cudaMalloc(&blk_flags, 256 * sizeof(int)));
+        GPP_TRY(cudaMemset(blk_flags, 0, 256 * sizeof(int)));
+        if (getenv("GPP_BLOCK_CTAS")) blk_ctas = atoi(getenv("GPP_BLOCK_CTAS"));
         panels = (T + PANEL_BLOCKS - 1) / PANEL_BLOCKS;
         ev_pf.resize(panels);
         ev_tu.resize(panels);
@@ -608,6 +846,8 @@ struct CholLookahead {
         ev_tu.clear();
         ev_m1.clear();
         ev_s1.clear();
+        if (blk_flags) cudaFree(blk_flags);
+        blk_flags = nullptr;
         if (fork) cudaEventDestroy(fork);
         if (join) cudaEventDestroy(join);
         if (inv_done) cudaEventDestroy(inv_done);
@@ -923,8 +1163,12 @@ inline cudaError_t potrf_lazy(double* A, double* M, int ld, int T, double* logde
         const int nend = (pend + PB < T) ? pend + PB : T;
         const int n2end = (nend + PB < T) ? nend + PB : T;
         const int buf = p & 1, slot = p & 3;
-        // ---- B(p): diagonal block on the chain (row limit = pend) ----
-        GPP_TRY(panel_factor(A, M, ld, pend, p0, pend, logdet_part, info, la.side, nullptr));
+        // ---- B(p): diagonal block on the chain: one dataflow launch (or the launch-per-step chain with row limit pend) ----
+        if (la.blk_ctas > 0 && pend - p0 <= 16)
+            GPP_TRY(launch_block_potrf(A, M, ld, p0, pend - p0, logdet_part, info, la.blk_flags, ++la.blk_epoch, la.blk_ctas,
+                                       la.side));
+        else
+            GPP_TRY(panel_factor(A, M, ld, pend, p0, pend, logdet_part, info, la.side, nullptr));
         if (pend < T) {
             const long long o = (long long)p0 * TILE * ld + (long long)p0 * TILE;
             GPP_TRY(trtri_doubling(A + o, M + o, X + o, ld, pend - p0, la.side, nullptr));
