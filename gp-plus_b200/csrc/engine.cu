@@ -94,6 +94,7 @@ struct gpp_handle {
     gpp_timings tm;
     CholLookahead la;
     bool use_lookahead = true;
+    int small_block = 0;     // T <= 16: CTAs of the one-launch factorisation (GPP_SMALL_BLOCK; 0 = launch chain)
     OzCtx* oz = nullptr;     // INT8-sliced tcgen05 path of the O(N^3) stages (large problems; GPP_FP64=dmma turns it off)
     // CUDA-graph replay of one whole evaluation (small problems are launch-bound): [want_grad]
     cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
@@ -392,6 +393,7 @@ extern "C" int gpp_create(const gpp_problem* p, int device, gpp_handle** out) {
         h->use_graph = h->T <= 16;  // N <= 2048: an evaluation is a chain of ~25-100 tiny launches
         if ((e = getenv("GPP_GRAPH")) != nullptr) h->use_graph = atoi(e) != 0;
         if ((e = getenv("GPP_EARLY_OUT")) != nullptr) h->early_out = atoi(e) != 0;
+        if ((e = getenv("GPP_SMALL_BLOCK")) != nullptr) h->small_block = atoi(e);
     }
     CKH(h->la.init(h->T));
     {
@@ -597,7 +599,14 @@ static int stage_factor(gpp_handle* h) {
         CK(launch_cov(ca, h->kernel, h->st));
     }
     mark(h, EV_COV);
-    if (h->use_lookahead && h->oz && h->oz->ready && h->oz->lazy && h->T >= 3 * OzCtx::LAZY_PB)
+    if (h->small_block > 0 && h->T <= 16) {
+        // small problems: the whole factorisation is one dataflow launch (block_potrf_kernel) instead of a chain of
+        // T leaf / TRSM / update launches.  Inside a captured graph the launch arguments are frozen, so the tile flags
+        // are cleared by a memset node and the epoch is constant.
+        CK(cudaMemsetAsync(h->la.blk_flags, 0, 256 * sizeof(int), h->st));
+        CK(launch_block_potrf(h->A, h->M, (int)h->np, 0, h->T, h->logdet_part, h->info, h->la.blk_flags, 1, h->small_block,
+                              h->st));
+    } else if (h->use_lookahead && h->oz && h->oz->ready && h->oz->lazy && h->T >= 3 * OzCtx::LAZY_PB)
         CK(potrf_lazy(h->A, h->M, (int)h->np, h->T, h->logdet_part, h->info, h->st, h->la, h->S, *h->oz));
     else if (h->use_lookahead)
         CK(potrf_lookahead(h->A, h->M, (int)h->np, h->T, h->logdet_part, h->info, h->st, h->la, h->S, h->oz));

@@ -121,3 +121,35 @@ def test_ill_conditioned_covariance_on_both_arithmetics():
         g = np.concatenate([out["d_w"], [out["d_sigma_f2"]], out["d_noise"], out["d_beta"]])
         # the noise gradient is 0.5 tr(K^-1 - alpha alpha^T) ~ 1e10 here and dominates the max-norm
         assert np.max(np.abs(g - gr)) <= 1e-8 * np.max(np.abs(gr)), (mode, np.max(np.abs(g - gr)), np.max(np.abs(gr)))
+
+
+def test_block_dataflow_factorisation_matches_the_launch_chain():
+    """potrf_lazy factors the diagonal block of every panel in one dataflow launch (block_potrf_kernel: left-looking
+    tiles handed over through flags); GPP_BLOCK_CTAS=0 selects the launch-per-step chain it replaces.  Same arithmetic
+    in a different summation order: the two must agree far inside the parity tolerance."""
+    import os
+    n = 5120   # T = 40 >= 36: the lazy-panel path
+    thetas = W.c4_theta_points(W.c4_model(256))
+    hyp = W.c4_natural(thetas[1])
+    outs = []
+    for ctas in ("24", "0"):
+        old = os.environ.get("GPP_BLOCK_CTAS")
+        os.environ["GPP_BLOCK_CTAS"] = ctas
+        try:
+            eng = _engine(n)
+            try:
+                outs.append(eng.mll_grad(hyp, want_grad=True))
+            finally:
+                eng.close()
+        finally:
+            if old is None:
+                del os.environ["GPP_BLOCK_CTAS"]
+            else:
+                os.environ["GPP_BLOCK_CTAS"] = old
+    a, b = outs
+    assert abs(a["nll"] - b["nll"]) <= 1e-11 * abs(b["nll"]), (a["nll"], b["nll"])
+    ga = np.concatenate([a["d_w"], [a["d_sigma_f2"]], a["d_noise"], a["d_beta"]])
+    gb = np.concatenate([b["d_w"], [b["d_sigma_f2"]], b["d_noise"], b["d_beta"]])
+    assert np.max(np.abs(ga - gb)) <= 1e-10 * np.max(np.abs(gb))
+    ref = O.mll(W.c4_oracle_problem(n), hyp, want_grad=True)
+    _check(a, ref, "n=5120 block dataflow")
