@@ -415,7 +415,16 @@ extern "C" int gpp_create(const gpp_problem* p, int device, gpp_handle** out) {
             if ((e = getenv("GPP_OZ_INNER")) != nullptr) h->oz->inner_min_k = atoi(e);
             if ((e = getenv("GPP_OZ_LAZY")) != nullptr) h->oz->lazy = atoi(e);
             if ((e = getenv("GPP_OZ_STAGGER")) != nullptr) h->oz->stagger = atoi(e);
-            CKH(h->oz->init((int)h->np));
+            cudaError_t oe = h->oz->init((int)h->np);
+            if (oe == cudaErrorMemoryAllocation) {
+                // the digit planes (3 x 7 Np^2 bytes) do not fit next to the FP64 work matrices: stay on DMMA
+                cudaGetLastError();
+                h->oz->destroy();
+                delete h->oz;
+                h->oz = nullptr;
+            } else {
+                CKH(oe);
+            }
         }
     }
 

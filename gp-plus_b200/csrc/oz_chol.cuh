@@ -283,7 +283,7 @@ inline cudaError_t oz_trtri_level(OzCtx& oz, const double* L, double* M, double*
     return cudaSuccess;
 }
 
-inline bool oz_use_lauum(const OzCtx* oz, int T) { return oz && oz->ready && T >= 24 && T <= 128; }
+inline bool oz_use_lauum(const OzCtx* oz, int T) { return oz && oz->ready && T >= 24; }
 
 // Kinv (lower tiles) = M^T M, M lower triangular
 inline cudaError_t oz_lauum(OzCtx& oz, const double* M, double* Kinv, int ld, int T, cudaStream_t st) {
@@ -301,7 +301,15 @@ inline cudaError_t oz_lauum(OzCtx& oz, const double* M, double* Kinv, int ld, in
     op.klo_c = 0;
     op.khi_sel = KSEL_CONST;
     op.khi_c = T;
-    return launch_oz_gemm(oz.mPB_a, oz.mPB_b, op, 1, st);
+    // K ranges longer than 128 blocks (N > 16384) are accumulated in segments: |digit| <= 128, so 16384 products per
+    // int32 accumulation cannot overflow
+    for (int k0 = 0; k0 < T; k0 += 128) {
+        op.k_min = k0;
+        op.k_max = (k0 + 128 < T) ? k0 + 128 : T;
+        op.beta = (k0 == 0) ? 0.0 : 1.0;
+        if ((e = launch_oz_gemm(oz.mPB_a, oz.mPB_b, op, 1, st)) != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 }  // namespace gpp

@@ -71,6 +71,8 @@ struct OzGemmOp {
     int tiles_m, tiles_n, tiles_m_last;
     int map, lower_filter, lower_off;
     int klo_sel, klo_c, khi_sel, khi_c;
+    int k_min, k_max;                // clamp of the K range in 128-blocks (k_max <= 0: none): long accumulations are cut
+                                     // into launches of <= 128 blocks so that an int32 accumulator cannot overflow
     double alpha, beta;
     int n_tiles;                     // 128x128 tiles per batch entry (set by launch_oz_gemm)
     int stagger_ns;                  // > 0: CTA b of the first wave starts (b mod 148) / 148 of this many ns late, so that
@@ -184,7 +186,11 @@ __device__ __forceinline__ bool oz_decode(const OzGemmOp& op, int tile_id, int t
 }
 __device__ __forceinline__ int oz_chunks(const OzGemmOp& op, int ti, int tj, int& klo) {
     klo = op.klo_c + (op.klo_sel == KSEL_TI ? ti : (op.klo_sel == KSEL_TJ ? tj : 0));
-    const int khi = op.khi_c + (op.khi_sel == KSEL_TI ? ti : (op.khi_sel == KSEL_TJ ? tj : 0));
+    int khi = op.khi_c + (op.khi_sel == KSEL_TI ? ti : (op.khi_sel == KSEL_TJ ? tj : 0));
+    if (op.k_max > 0) {
+        klo = klo > op.k_min ? klo : op.k_min;
+        khi = khi < op.k_max ? khi : op.k_max;
+    }
     return (khi > klo) ? (khi - klo) * (TILE / OZ_BK) : 0;
 }
 
