@@ -17,13 +17,15 @@
 // operand reads, 6 KB per MMA at 128 B/clk), N = 128: 64 cycles, N = 256: 128 cycles (both = 4.5 POPS).  N = 128 is
 // the narrowest shape that reaches the peak, and TMEM holds four 128-column accumulators, so a 128x128 output tile
 // is produced in two passes over K:
-//   pass 0: levels 0..3 (10 plane pairs, planes 0..3 of both operands),  C  = beta C + alpha * (...)
-//   pass 1: levels 4..6 (18 plane pairs, planes 0..6),                   C += alpha * (...)
+//   pass 0: levels 0..2 ( 6 plane pairs, planes 0..2 of both operands),  C  = beta C + alpha * (...)
+//   pass 1: levels 3..6 (22 plane pairs, planes 0..6),                   C += alpha * (...)
+// (20 plane tiles streamed per K chunk; the 4 + 3 split streams 22 and measured 1-5 % slower in isolation: the kernel
+// is bound by the bytes an SM ingests from L2)
 //
 // One CTA per SM (all of TMEM, 225 KB of shared memory), each looping over a few output tiles:
 //   warp 0 (one lane)  TMA producer: per 64-byte K chunk the planes the pass needs (128 rows x 64 B, SWIZZLE_64B),
 //                      2-slot mbarrier ring
-//   warp 1 (one lane)  tcgen05.mma.cta_group::1.kind::i8, M = N = 128, K = 32; tcgen05.commit frees the slot /
+//   warp 1 (one lane)  tcgen05.mma.cta_group::1.kind::i8, M = N = 128, K = 32 (12 / 44 per slot); tcgen05.commit frees the slot /
 //                      publishes the accumulators
 //   warps 2-9          epilogue: tcgen05.ld 16x256b (two warps per TMEM lane quarter, 64 columns each; a quad of threads
 //                      owns 64 contiguous bytes of a C row), Horner over the levels in FP64, power-of-two row /
@@ -39,7 +41,11 @@
 namespace gpp {
 
 constexpr int OZ_S = 7;            // digit planes per operand
-constexpr int OZ_L0 = 4;           // levels of pass 0 (accumulators 0..3); pass 1: levels 4..6 (accumulators 0..2)
+#ifndef GPP_OZ_L0
+#define GPP_OZ_L0 3
+#endif
+constexpr int OZ_L0 = GPP_OZ_L0;   // pass 0: levels 0 .. L0-1 (planes 0 .. L0-1), pass 1: levels L0 .. 6 (all planes)
+constexpr int OZ_NACC = (OZ_L0 > OZ_S - OZ_L0) ? OZ_L0 : OZ_S - OZ_L0;   // accumulators live at a time
 constexpr int OZ_BM = 128;         // output rows per work item (UMMA M)
 constexpr int OZ_BN = 128;         // output columns per work item (UMMA N)
 constexpr int OZ_BK = 64;          // K bytes (= int8 elements) per ring slot = swizzle width
@@ -54,7 +60,7 @@ constexpr int OZ_THREADS = 32 * (2 + OZ_EPI_WARPS);
 constexpr int OZ_TMEM_COLS = 512;
 static_assert(OZ_SMEM_BYTES <= 232448, "oz_gemm shared memory exceeds the 227 KB per-CTA limit");
 static_assert(OZ_BK == 32 || OZ_BK == 64 || OZ_BK == 128, "K chunk must equal a swizzle width");
-static_assert(OZ_L0 * OZ_BN <= OZ_TMEM_COLS && (OZ_S - OZ_L0) <= OZ_L0, "accumulators must fit in TMEM");
+static_assert(OZ_NACC * OZ_BN <= OZ_TMEM_COLS && OZ_L0 >= 1 && OZ_L0 < OZ_S, "accumulators must fit in TMEM");
 
 // same K-range / tile-map vocabulary as GemmOp (dgemm_dmma.cuh); a work item is one 128x128 tile
 struct OzGemmOp {
@@ -350,8 +356,8 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const double* sbp = op.b_scale + op.b_row0 + z * op.b_zs_row + tj * TILE + ch * 64 + cq;
             for (int pass = 0; pass < 2; pass++) {
                 const double beta = pass == 0 ? op.beta : 1.0;
-                // 256^-(lvl+2) of the pass's lowest level: 2^-16 (pass 0), 2^-48 (pass 1)
-                const double ps = alpha * (pass == 0 ? (1.0 / 65536.0) : (1.0 / 281474976710656.0));
+                // 256^-(lvl+2) of the pass's lowest level: 2^-16 (pass 0), 2^-(16 + 8 L0) (pass 1)
+                const double ps = alpha * (pass == 0 ? (1.0 / 65536.0) : (1.0 / 65536.0) / (double)(1ull << (8 * OZ_L0)));
                 // step = (row half rh, 32-column group cg): rows q*32 + 16 rh + r_in + {0, 8}, columns 32 cg + 8 j + cq + {0,1}.
                 // C and the scales of a step are fetched one step ahead (for the first step: before the pass's MMAs
                 // have finished), so that their latency is not paid per element
@@ -382,15 +388,21 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int step = 0; step < 4; step++) {
                     const int rh = step >> 1, cg = step & 1;
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32 + rh * 16) << 16) + ch * 64 + cg * 32;
-                    int v[OZ_L0][16];
+                    int v[OZ_NACC][16];
                     if (pass == 0) {
 #pragma unroll
                         for (int a = 0; a < OZ_L0; a++) tmem_ld_16x256b_x4(taddr + a * OZ_BN, v[a]);
+#pragma unroll
+                        for (int a = OZ_L0; a < OZ_NACC; a++)
+#pragma unroll
+                            for (int e = 0; e < 16; e++) v[a][e] = 0;
                     } else {
 #pragma unroll
                         for (int a = 0; a < OZ_S - OZ_L0; a++) tmem_ld_16x256b_x4(taddr + a * OZ_BN, v[a]);
 #pragma unroll
-                        for (int e = 0; e < 16; e++) v[OZ_L0 - 1][e] = 0;
+                        for (int a = OZ_S - OZ_L0; a < OZ_NACC; a++)
+#pragma unroll
+                            for (int e = 0; e < 16; e++) v[a][e] = 0;
                     }
                     tmem_ld_wait();
                     double2 o[8];
@@ -398,9 +410,9 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int j = 0; j < 4; j++) {
 #pragma unroll
                         for (int h = 0; h < 2; h++) {   // h = 0: row r_in, h = 1: row r_in + 8
-                            double s0 = (double)v[OZ_L0 - 1][4 * j + 2 * h], s1 = (double)v[OZ_L0 - 1][4 * j + 2 * h + 1];
+                            double s0 = (double)v[OZ_NACC - 1][4 * j + 2 * h], s1 = (double)v[OZ_NACC - 1][4 * j + 2 * h + 1];
 #pragma unroll
-                            for (int a = OZ_L0 - 2; a >= 0; a--) {
+                            for (int a = OZ_NACC - 2; a >= 0; a--) {
                                 s0 = fma(s0, 1.0 / 256.0, (double)v[a][4 * j + 2 * h]);
                                 s1 = fma(s1, 1.0 / 256.0, (double)v[a][4 * j + 2 * h + 1]);
                             }
