@@ -414,6 +414,7 @@ extern "C" int gpp_create(const gpp_problem* p, int device, gpp_handle** out) {
             if ((e = getenv("GPP_OZ_NEXT")) != nullptr) h->oz->next_on_oz = atoi(e);
             if ((e = getenv("GPP_OZ_INNER")) != nullptr) h->oz->inner_min_k = atoi(e);
             if ((e = getenv("GPP_OZ_LAZY")) != nullptr) h->oz->lazy = atoi(e);
+            if ((e = getenv("GPP_OZ_LAZY_MIN")) != nullptr) h->oz->lazy_min_tiles = atoi(e);
             if ((e = getenv("GPP_OZ_STAGGER")) != nullptr) h->oz->stagger = atoi(e);
             cudaError_t oe = h->oz->init((int)h->np);
             if (oe == cudaErrorMemoryAllocation) {
@@ -615,7 +616,7 @@ static int stage_factor(gpp_handle* h) {
         CK(cudaMemsetAsync(h->la.blk_flags, 0, 256 * sizeof(int), h->st));
         CK(launch_block_potrf(h->A, h->M, (int)h->np, 0, h->T, h->logdet_part, h->info, h->la.blk_flags, 1, h->small_block,
                               h->st));
-    } else if (h->use_lookahead && h->oz && h->oz->ready && h->oz->lazy && h->T >= 3 * OzCtx::LAZY_PB)
+    } else if (h->use_lookahead && h->oz && h->oz->ready && h->oz->lazy && h->T >= h->oz->lazy_min_tiles)
         CK(potrf_lazy(h->A, h->M, (int)h->np, h->T, h->logdet_part, h->info, h->st, h->la, h->S, *h->oz));
     else if (h->use_lookahead)
         CK(potrf_lookahead(h->A, h->M, (int)h->np, h->T, h->logdet_part, h->info, h->st, h->la, h->S, h->oz));

@@ -25,6 +25,8 @@ struct OzCtx {
     // against its explicit inverse W = L_pp^-1 by one integer GEMM.  W's digit planes, double-buffered by panel parity:
     static constexpr int LAZY_PB = 12;     // panel width in 128-tiles
     int lazy = 1;
+    int lazy_min_tiles = 96;       // from N = 12288; below, 512-column panels of the look-ahead schedule keep the chain
+                                   // shorter (measured: N = 8192 12.7 vs 14.0 ms, N = 12288 28.5 vs 27.9, N = 16384 55.3 vs 54.4)
     int stagger = 6000;            // ns per 128-block of K: estimated duration of one 128x128 item, see OzGemmOp.stagger_ns
     OzPlanes PW[2];
     CUtensorMap mPW_b[2];

@@ -128,24 +128,26 @@ def test_block_dataflow_factorisation_matches_the_launch_chain():
     tiles handed over through flags); GPP_BLOCK_CTAS=0 selects the launch-per-step chain it replaces.  Same arithmetic
     in a different summation order: the two must agree far inside the parity tolerance."""
     import os
-    n = 5120   # T = 40 >= 36: the lazy-panel path
+    n = 5120   # T = 40; GPP_OZ_LAZY_MIN lowers the size threshold (96 tiles) of the lazy-panel path for this test
     thetas = W.c4_theta_points(W.c4_model(256))
     hyp = W.c4_natural(thetas[1])
     outs = []
-    for ctas in ("24", "0"):
-        old = os.environ.get("GPP_BLOCK_CTAS")
-        os.environ["GPP_BLOCK_CTAS"] = ctas
-        try:
+    saved = {k: os.environ.get(k) for k in ("GPP_BLOCK_CTAS", "GPP_OZ_LAZY_MIN")}
+    os.environ["GPP_OZ_LAZY_MIN"] = "36"
+    try:
+        for ctas in ("24", "0"):
+            os.environ["GPP_BLOCK_CTAS"] = ctas
             eng = _engine(n)
             try:
                 outs.append(eng.mll_grad(hyp, want_grad=True))
             finally:
                 eng.close()
-        finally:
-            if old is None:
-                del os.environ["GPP_BLOCK_CTAS"]
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
             else:
-                os.environ["GPP_BLOCK_CTAS"] = old
+                os.environ[k] = v
     a, b = outs
     assert abs(a["nll"] - b["nll"]) <= 1e-11 * abs(b["nll"]), (a["nll"], b["nll"])
     ga = np.concatenate([a["d_w"], [a["d_sigma_f2"]], a["d_noise"], a["d_beta"]])

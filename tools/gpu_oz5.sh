@@ -1,17 +1,17 @@
 #!/bin/bash
-# INT8-sliced vs DMMA at mid sizes (which arithmetic should be the default where)
+# INT8-sliced vs DMMA at mid sizes (which arithmetic should be the default where), lazy panels on / off
 mkdir -p gpurun_out
-for n in 2048 3072 4096 6144 8192 12288; do
-for mode in int8 dmma; do
-  if [ $mode = int8 ]; then M=1; else M=0; fi
-  python - <<PY 2>&1 | tail -1
+for n in 3072 4096 6144 8192 12288; do
+for cfg in "1 1" "1 0" "0 1"; do
+  set -- $cfg
+  GPP_OZ_LAZY=$2 python - <<PY 2>&1 | tail -1
 import sys, time
 sys.path[:0] = ['.', 'gp-plus_b200']
 import numpy as np
 import bench_workloads as W
 from gpplus_b200 import _engine as E
 n = $n
-E.set_fp64_mode($M)
+E.set_fp64_mode($1)
 X, y = W.c4_workload(n)
 ys = (y - y.min()) / (y.max() - y.min())
 eng = E.Engine(xq=X, y=ys, kernel=E.KERNEL_MATERN52, n_noise=1, n_mean=1, device=0)
@@ -22,7 +22,7 @@ for k in range(6):
     t = eng.timings()
     if k >= 2: outs.append(t)
 tot = np.median([t['total'] for t in outs])
-print("n=%5d %s (mode reported %d): total %.3f ms  chol %.3f trtri %.3f lauum %.3f  nll %.12e" % (n, '$mode', eng.fp64_mode(), tot, outs[-1]['cholesky'], outs[-1]['trtri'], outs[-1]['lauum'], o['nll']))
+print("n=%5d fp64_mode %d lazy $2: total %.3f ms  chol %.3f trtri %.3f lauum %.3f  nll %.12e" % (n, eng.fp64_mode(), tot, outs[-1]['cholesky'], outs[-1]['trtri'], outs[-1]['lauum'], o['nll']))
 eng.close()
 PY
 done
