@@ -1148,9 +1148,9 @@ inline cudaError_t trtri_late(const double* L, double* M, double* X, int ld, int
 //   m3(p)  update of everything to the right of block p+3, issued after the urgent pieces of panel p+1
 inline cudaError_t potrf_lazy(double* A, double* M, int ld, int T, double* logdet_part, int* info, cudaStream_t st,
                               CholLookahead& la, double* X, OzCtx& oz) {
-    const int PB = OzCtx::LAZY_PB;
+    const int PB = oz.lazy_pb;
     const int NP = (T + PB - 1) / PB;
-    if (NP > la.panels) return cudaErrorInvalidValue;
+    if (NP > la.panels || PB > OzCtx::LAZY_PB || PB < 2) return cudaErrorInvalidValue;
     const int H = trtri_split_point(T);
     const bool overlap = g_overlap_inverse && X != nullptr && H > 0 && NP > 1;
     la.inv_pending = false;

@@ -415,6 +415,7 @@ extern "C" int gpp_create(const gpp_problem* p, int device, gpp_handle** out) {
             if ((e = getenv("GPP_OZ_INNER")) != nullptr) h->oz->inner_min_k = atoi(e);
             if ((e = getenv("GPP_OZ_LAZY")) != nullptr) h->oz->lazy = atoi(e);
             if ((e = getenv("GPP_OZ_LAZY_MIN")) != nullptr) h->oz->lazy_min_tiles = atoi(e);
+            if ((e = getenv("GPP_OZ_LAZY_PB")) != nullptr) h->oz->lazy_pb = std::min(std::max(atoi(e), 2), OzCtx::LAZY_PB);
             if ((e = getenv("GPP_OZ_STAGGER")) != nullptr) h->oz->stagger = atoi(e);
             cudaError_t oe = h->oz->init((int)h->np);
             if (oe == cudaErrorMemoryAllocation) {
@@ -816,7 +817,7 @@ static int run_eval(gpp_handle* h, const gpp_hyper* hy, int want_grad, int first
             if (rc != GPP_OK) return rc;
             mark(h, EV_END);
             CK(cudaStreamSynchronize(h->st));
-            if (h->la.timeline) h->la.dump_timeline((h->T + OzCtx::LAZY_PB - 1) / OzCtx::LAZY_PB);
+            if (h->la.timeline) h->la.dump_timeline(h->oz ? (h->T + h->oz->lazy_pb - 1) / h->oz->lazy_pb : h->la.panels);
             info = failed ? failed : (int)h->res_host[2];
         } else {
             int rc = enqueue_eval(h, want_grad);

@@ -23,7 +23,8 @@ struct OzCtx {
     double* pscale[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // lazy panels: only the diagonal block of a panel is factored on the latency-bound chain; the rows below are solved
     // against its explicit inverse W = L_pp^-1 by one integer GEMM.  W's digit planes, double-buffered by panel parity:
-    static constexpr int LAZY_PB = 12;     // panel width in 128-tiles
+    static constexpr int LAZY_PB = 16;     // widest panel in 128-tiles (sizes the W planes)
+    int lazy_pb = 12;                      // panel width used (GPP_OZ_LAZY_PB)
     int lazy = 1;
     int lazy_min_tiles = 96;       // from N = 12288; below, 512-column panels of the look-ahead schedule keep the chain
                                    // shorter (measured: N = 8192 12.7 vs 14.0 ms, N = 12288 28.5 vs 27.9, N = 16384 55.3 vs 54.4)
