@@ -8,6 +8,8 @@ mean / variance -- is a call into ``libgpplus_b200.so``.
 """
 from __future__ import annotations
 
+import contextlib
+
 import math
 import threading
 from typing import List, Optional, Tuple, Union
@@ -220,7 +222,22 @@ class GPR(Module):
         multi-start driver keeps one handle per in-flight restart and passes the same ``kwargs`` to all of them)."""
         return _engine.Engine(**(kwargs if kwargs is not None else self._engine_kwargs(dev)))
 
+    @contextlib.contextmanager
+    def engine_override(self, engine):
+        """Route every engine call of this model to ``engine`` inside the block (the closed-form objective is validated
+        against the torch path through a stub engine, optim/_fast_objective.self_check); the real engine, its
+        factorisation cache and the parameters are untouched."""
+        prev = getattr(self, "_engine_stub", None)
+        self._engine_stub = engine
+        try:
+            yield engine
+        finally:
+            self._engine_stub = prev
+            self._factor_key = None
+
     def _get_engine(self) -> "_engine.Engine":
+        if getattr(self, "_engine_stub", None) is not None:
+            return self._engine_stub
         dev = get_default_device()
         if self._engine is not None and self._engine_device == dev and self._engine.n_pass == self._latent_passes():
             return self._engine

@@ -375,28 +375,30 @@ def self_check(likobj, fast: FastObjective, trials: int = 2, tol: Optional[float
     stub = _StubEngine(len(model._quant_columns()), 0 if table is None else int(table.shape[1]),
                        0 if table is None else int(table.shape[0]),
                        int(model.likelihood.noise_covar.raw_noise.numel()), n_mean)
-    saved = model.__dict__.get("_get_engine")
+    # one verdict per model structure: the layout depends on which parameters exist / are frozen, not on their values
+    sig = (tuple((n, tuple(p_.shape), str(p_.dtype), bool(p_.requires_grad)) for n, p_ in model.named_parameters()),
+           bool(likobj.add_prior), tuple(np.ravel(likobj.regularization_parameter).tolist()), float(tol), int(trials))
+    cache = model.__dict__.setdefault("_fast_check_cache", {})
+    if sig in cache:
+        return cache[sig]
     keep = likobj.pack_parameters().copy()
     rng = np.random.RandomState(1)
     ok = True
     try:
-        model.__dict__["_get_engine"] = lambda: stub
-        for _ in range(trials):
-            x = keep + 0.5 * rng.randn(keep.shape[0])
-            f_ref, g_ref = likobj.fun(x)
-            f, g = fast.fun(x, stub.mll_grad)
-            scale = max(1.0, abs(f_ref))
-            gscale = max(1.0, float(np.max(np.abs(g_ref))))
-            if not (abs(f - f_ref) <= tol * scale and float(np.max(np.abs(g - g_ref))) <= tol * gscale):
-                ok = False
-                break
+        with model.engine_override(stub):
+            for _ in range(trials):
+                x = keep + 0.5 * rng.randn(keep.shape[0])
+                f_ref, g_ref = likobj.fun(x)
+                f, g = fast.fun(x, stub.mll_grad)
+                scale = max(1.0, abs(f_ref))
+                gscale = max(1.0, float(np.max(np.abs(g_ref))))
+                if not (abs(f - f_ref) <= tol * scale and float(np.max(np.abs(g - g_ref))) <= tol * gscale):
+                    ok = False
+                    break
     except Exception:
         ok = False
     finally:
-        if saved is None:
-            model.__dict__.pop("_get_engine", None)
-        else:
-            model.__dict__["_get_engine"] = saved
         likobj._load(keep)
         model._factor_key = None
+    cache[sig] = ok
     return ok
