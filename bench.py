@@ -392,7 +392,9 @@ def run_ours(args):
         peak_i8 = E.probe_i8(256, 4096, local)     # raw tcgen05 kind::i8 issue rate, whole GPU, measured live
         peak_i8_n128 = E.probe_i8(128, 4096, local)
         pairs = 28.0                                # int8 multiply-adds per FP64-equivalent multiply-add
-        ach_i8 = pairs * n3 / (tensor_ms * 1e-3) / 1e12
+        kinv_pairs = {7: 28.0, 6: 21.0, 5: 15.0}.get(int(os.environ.get("GPP_OZ_KINV_LEVELS", "6")), 28.0)  # K^-1 product
+        ops_eval = (2.0 * pairs + kinv_pairs) * n3 / 3.0   # potrf + trtri with 28 plane pairs, K^-1 with 21
+        ach_i8 = ops_eval / (tensor_ms * 1e-3) / 1e12
         roofline = {
             "bound": "tensor", "kernel": "oz_gemm_kernel (tcgen05.mma kind::i8 M=N=128 K=32, TMA-fed, int32 TMEM "
                                          "accumulators; 7 digit planes per operand, 28 plane pairs)",
@@ -401,15 +403,16 @@ def run_ours(args):
             "peak_source": "measured live: gpp_probe_i8 (tcgen05.mma kind::i8 M=128 N=256 issued back to back on "
                            "resident operands, 148 SMs); the N=128 shape the kernel uses issues at %.0f TOP/s; "
                            "MEASURED_PEAKS.json has no INT8 entry (nominal 4500)" % peak_i8_n128,
-            "algorithmic_ops_per_eval": pairs * n3,
-            "basis": "all O(N^3) work of one step: N^3 FP64-equivalent flops (potrf + trtri + lauum, N^3/3 each) = 28 N^3 "
-                     "int8 ops, over the CUDA-event time of those three stages (digit-plane splits, DMMA panel chain, "
-                     "leaf kernels and launch gaps included)",
-            "largest_launch": {"what": "K^-1 = L^-T L^-1: transposed digit-plane split + one oz_gemm launch",
-                               "algorithmic_ops": pairs * n3 / 3, "ms": stage["lauum"],
-                               "achieved": pairs * n3 / 3 / (stage["lauum"] * 1e-3) / 1e12,
-                               "frac": pairs * n3 / 3 / (stage["lauum"] * 1e-3) / 1e12 / peak_i8},
-            "other_denominators": _other_denominators(ach_i8, pairs * n3 / 3 / (stage["lauum"] * 1e-3) / 1e12),
+            "algorithmic_ops_per_eval": ops_eval,
+            "basis": "all O(N^3) work of one step: N^3 FP64-equivalent flops (potrf + trtri + lauum, N^3/3 each) = "
+                     "(28 + 28 + 21) N^3 / 3 int8 ops actually issued (28 plane pairs per product; K^-1, which only feeds the "
+                     "gradient trace, keeps 21), over the CUDA-event time of those three stages (digit-plane splits, DMMA "
+                     "panel chain, leaf kernels and launch gaps included)",
+            "largest_launch": {"what": "K^-1 = L^-T L^-1: transposed digit-plane split + one oz_gemm launch, %d plane pairs" % kinv_pairs,
+                               "algorithmic_ops": kinv_pairs * n3 / 3, "ms": stage["lauum"],
+                               "achieved": kinv_pairs * n3 / 3 / (stage["lauum"] * 1e-3) / 1e12,
+                               "frac": kinv_pairs * n3 / 3 / (stage["lauum"] * 1e-3) / 1e12 / peak_i8},
+            "other_denominators": _other_denominators(ach_i8, kinv_pairs * n3 / 3 / (stage["lauum"] * 1e-3) / 1e12),
             "fp64_equivalent": {"achieved_tflops": achieved, "fp64_tensor_peak_tflops": peak,
                                 "ratio_to_fp64_tensor_peak": achieved / peak,
                                 "peak_source": "torch.matmul f64 8192^3 best of 10 (cuBLAS DGEMM), measured live"},

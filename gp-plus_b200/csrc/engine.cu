@@ -414,6 +414,7 @@ extern "C" int gpp_create(const gpp_problem* p, int device, gpp_handle** out) {
             if ((e = getenv("GPP_OZ_NEXT")) != nullptr) h->oz->next_on_oz = atoi(e);
             if ((e = getenv("GPP_OZ_INNER")) != nullptr) h->oz->inner_min_k = atoi(e);
             if ((e = getenv("GPP_OZ_LAZY")) != nullptr) h->oz->lazy = atoi(e);
+            if ((e = getenv("GPP_OZ_KINV_LEVELS")) != nullptr) h->oz->kinv_levels = atoi(e);
             if ((e = getenv("GPP_OZ_LAZY_MIN")) != nullptr) h->oz->lazy_min_tiles = atoi(e);
             if ((e = getenv("GPP_OZ_LAZY_PB")) != nullptr) h->oz->lazy_pb = std::min(std::max(atoi(e), 2), OzCtx::LAZY_PB);
             if ((e = getenv("GPP_OZ_STAGGER")) != nullptr) h->oz->stagger = atoi(e);

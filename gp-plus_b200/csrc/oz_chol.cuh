@@ -26,6 +26,9 @@ struct OzCtx {
     static constexpr int LAZY_PB = 16;     // widest panel in 128-tiles (sizes the W planes)
     int lazy_pb = 12;                      // panel width used (GPP_OZ_LAZY_PB)
     int lazy = 1;
+    int kinv_levels = 6;           // significance levels of K^-1 = M^T M (GPP_OZ_KINV_LEVELS): its only consumer is the
+                                   // gradient trace (tolerance 1e-8 of the gradient's max-norm); 21 of 28 plane pairs
+                                   // move the gradient by ~1e-12 (tools/ozaki_numerics.py, LEVELS_KINV)
     int lazy_min_tiles = 96;       // from N = 12288; below, 512-column panels of the look-ahead schedule keep the chain
                                    // shorter (measured: N = 8192 12.7 vs 14.0 ms, N = 12288 28.5 vs 27.9, N = 16384 55.3 vs 54.4)
     int stagger = 6000;            // ns per 128-block of K: estimated duration of one 128x128 item, see OzGemmOp.stagger_ns
@@ -304,6 +307,7 @@ inline cudaError_t oz_lauum(OzCtx& oz, const double* M, double* Kinv, int ld, in
     op.klo_c = 0;
     op.khi_sel = KSEL_CONST;
     op.khi_c = T;
+    op.levels = oz.kinv_levels;
     // K ranges longer than 128 blocks (N > 16384) are accumulated in segments: |digit| <= 128, so 16384 products per
     // int32 accumulation cannot overflow
     for (int k0 = 0; k0 < T; k0 += 128) {

@@ -77,6 +77,9 @@ struct OzGemmOp {
     int tiles_m, tiles_n, tiles_m_last;
     int map, lower_filter, lower_off;
     int klo_sel, klo_c, khi_sel, khi_c;
+    int levels;                      // significance levels kept (0 = all 7): pairs with i + j >= levels and the planes they
+                                     // alone would need are skipped.  K^-1 feeds only the gradient trace (tolerance 1e-8)
+                                     // and runs with 6 (21 pairs); everything that feeds the objective keeps 7
     int k_min, k_max;                // clamp of the K range in 128-blocks (k_max <= 0: none): long accumulations are cut
                                      // into launches of <= 128 blocks so that an int32 accumulator cannot overflow
     double alpha, beta;
@@ -215,6 +218,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int z = blockIdx.y;
     const int tm = (z == (int)gridDim.y - 1) ? op.tiles_m_last : op.tiles_m;
     const int n_items = op.n_tiles;
+    const int nlev = (op.levels > OZ_L0 && op.levels < OZ_S) ? op.levels : OZ_S;   // levels kept (pass 1: planes 0 .. nlev-1)
     if (op.stagger_ns > 0 && blockIdx.x < GEMM_NUM_SMS) {
         for (int w = (int)((long long)blockIdx.x * op.stagger_ns / GEMM_NUM_SMS); w > 0; w -= 1000)
             __nanosleep(w > 1000 ? 1000 : w);
@@ -250,7 +254,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int ka = op.a_k0 + z * op.a_zs_k + klo * TILE;
                 const int kb = op.b_k0 + z * op.b_zs_k + klo * TILE;
                 for (int pass = 0; pass < 2; pass++) {
-                    const int npl = pass == 0 ? OZ_L0 : OZ_S;
+                    const int npl = pass == 0 ? OZ_L0 : nlev;
                     for (int c = 0; c < nch; c++) {
                         mbar_wait(&empty[stage], phase ^ 1);
                         mbar_arrive_expect_tx(&full[stage], (uint32_t)npl * (OZ_A_TILE + OZ_B_TILE));
@@ -305,7 +309,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                                     for (int i = 0; i <= lvl; i++) {
                                         const int j = lvl - i;
-                                        if (i < OZ_S && j < OZ_S) {
+                                        if (i < OZ_S && j < OZ_S && lvl < nlev) {
                                             const uint64_t ad = oz_smem_desc(sa + i * OZ_A_TILE + ks * OZ_UMMA_K);
                                             const uint64_t bd = oz_smem_desc(sb + j * OZ_B_TILE + ks * OZ_UMMA_K);
                                             umma_i8(tmem_base + (lvl - OZ_L0) * OZ_BN, ad, bd, OZ_IDESC,
@@ -398,7 +402,14 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             for (int e = 0; e < 16; e++) v[a][e] = 0;
                     } else {
 #pragma unroll
-                        for (int a = 0; a < OZ_S - OZ_L0; a++) tmem_ld_16x256b_x4(taddr + a * OZ_BN, v[a]);
+                        for (int a = 0; a < OZ_S - OZ_L0; a++) {
+                            if (OZ_L0 + a < nlev) {
+                                tmem_ld_16x256b_x4(taddr + a * OZ_BN, v[a]);
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < 16; e++) v[a][e] = 0;
+                            }
+                        }
 #pragma unroll
                         for (int a = OZ_S - OZ_L0; a < OZ_NACC; a++)
 #pragma unroll

@@ -263,6 +263,22 @@ static int check_lauum(int n) {
     printf("lauum shape n=%d: |oz - dmma|max / |dmma|max = %.3e\n", n, worst / cmax);
     if (!(worst / cmax < 1e-13)) fails++;
     fflush(stdout);
+    for (int lv = 6; lv >= 5; lv--) {
+        // fewer significance levels (the K^-1 product of the engine keeps 6: it only feeds the gradient trace)
+        OzGemmOp o2 = op;
+        o2.levels = lv;
+        CHECK(launch_oz_gemm(tmA, tmB, o2, 1, 0));
+        CHECK(cudaDeviceSynchronize());
+        CHECK(cudaMemcpy(C.data(), dC, sizeof(double) * n * n, cudaMemcpyDeviceToHost));
+        double w2 = 0.0;
+        for (int i = 0; i < n; i++)
+            for (int j = 0; j < n; j++) {
+                if (j / TILE > i / TILE) continue;
+                w2 = fmax(w2, fabs(C[(size_t)i * n + j] - R[(size_t)i * n + j]));
+            }
+        printf("   %d levels: |oz - dmma|max / |dmma|max = %.3e\n", lv, w2 / cmax);
+        if (!(w2 / cmax < (lv == 6 ? 1e-10 : 1e-8))) fails++;
+    }
     cudaFree(dM); cudaFree(dC); cudaFree(dR);
     free_planes(P);
     return fails;
@@ -396,6 +412,21 @@ static void perf(int n, int kblocks, int tri, int reps) {
     CHECK(cudaEventSynchronize(e1));
     cudaEventElapsedTime(&ms_oz, e0, e1);
     ms_oz /= reps;
+    float ms_lv[2] = {0.f, 0.f};
+    if (tri) {
+        for (int q = 0; q < 2; q++) {
+            OzGemmOp o2 = op;
+            o2.levels = 6 - q;
+            CHECK(launch_oz_gemm(tmA, tmB, o2, 1, 0));
+            cudaEventRecord(e0);
+            for (int i = 0; i < reps; i++) CHECK(launch_oz_gemm(tmA, tmB, o2, 1, 0));
+            cudaEventRecord(e1);
+            CHECK(cudaEventSynchronize(e1));
+            cudaEventElapsedTime(&ms_lv[q], e0, e1);
+            ms_lv[q] /= reps;
+        }
+        printf("   K^-1 shape with 6 levels (21 pairs): %.3f ms, 5 levels (15 pairs): %.3f ms\n", ms_lv[0], ms_lv[1]);
+    }
     GemmOp g = gemm_default();
     g.A = dA; g.lda = n; g.B = dA; g.ldb = n; g.C = dC; g.ldc = n;
     g.map = MAP_TRI; g.tiles_m = g.tiles_m_last = T; g.tiles_n = T;

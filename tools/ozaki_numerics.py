@@ -37,12 +37,16 @@ def split_rows(A):
     return planes, e
 
 
-def ozaki_abt(A, B):
+LEVELS_KINV = int(os.environ.get("LEVELS_KINV", LEVELS))   # levels kept in K^-1 = M^T M only
+
+
+def ozaki_abt(A, B, levels=None):
     """A [m,K] @ B[n,K]^T through digit planes."""
+    levels = LEVELS if levels is None else levels
     pa, ea = split_rows(A)
     pb, eb = split_rows(B)
     acc = np.zeros((A.shape[0], B.shape[0]))
-    for lvl in range(LEVELS - 1, -1, -1):       # small terms first
+    for lvl in range(levels - 1, -1, -1):       # small terms first
         t = np.zeros_like(acc)
         for i in range(min(lvl, S - 1) + 1):
             j = lvl - i
@@ -87,7 +91,7 @@ def trtri_doubling(L, nb, mm):
 def evaluate(K, r, mm, nb_chol, nb_inv):
     L = chol_blocked(K, nb_chol, mm)
     M = trtri_doubling(L, nb_inv, mm)
-    Kinv = mm(M.T, M.T)                                          # M^T M
+    Kinv = mm(M.T, M.T) if mm is not ozaki_abt else ozaki_abt(M.T, M.T, LEVELS_KINV)   # M^T M
     u = M @ r
     alpha = M.T @ u
     nll = 0.5 * (u @ u) + np.sum(np.log(np.diag(L))) + 0.5 * len(r) * np.log(2 * np.pi)
