@@ -38,6 +38,7 @@ def split_rows(A):
 
 
 LEVELS_KINV = int(os.environ.get("LEVELS_KINV", LEVELS))   # levels kept in K^-1 = M^T M only
+LEVELS_TRTRI = int(os.environ.get("LEVELS_TRTRI", LEVELS))  # levels kept in the triangular inverse only
 
 
 def ozaki_abt(A, B, levels=None):
@@ -90,7 +91,7 @@ def trtri_doubling(L, nb, mm):
 
 def evaluate(K, r, mm, nb_chol, nb_inv):
     L = chol_blocked(K, nb_chol, mm)
-    M = trtri_doubling(L, nb_inv, mm)
+    M = trtri_doubling(L, nb_inv, mm if mm is not ozaki_abt else (lambda A, B: ozaki_abt(A, B, LEVELS_TRTRI)))
     Kinv = mm(M.T, M.T) if mm is not ozaki_abt else ozaki_abt(M.T, M.T, LEVELS_KINV)   # M^T M
     u = M @ r
     alpha = M.T @ u
