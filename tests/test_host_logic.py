@@ -320,15 +320,19 @@ def test_closed_form_host_objective_equals_torch_path(kwargs):
     stub = FO._StubEngine(len(m._quant_columns()), 0 if table is None else int(table.shape[1]),
                           0 if table is None else int(table.shape[0]),
                           int(m.likelihood.noise_covar.raw_noise.numel()), n_mean)
-    m.__dict__["_get_engine"] = lambda: stub
+    assert FO.self_check(obj, fast, trials=3, tol=1e-12)   # second call: answered from the per-structure cache
+    assert len(m.__dict__["_fast_check_cache"]) == 1
     torch.manual_seed(3)
-    for k in range(20):
-        th = _sample_from_prior(m) * (1.0 if k < 15 else 2.5)
-        f_ref, g_ref = obj.fun(th)
-        f, g = fast.fun(th, stub.mll_grad)
-        if np.isfinite(f_ref):
-            assert abs(f - f_ref) <= 1e-12 * max(1.0, abs(f_ref))
-            assert np.max(np.abs(g - g_ref)) <= 1e-11 * max(1.0, np.max(np.abs(g_ref)))
+    with m.engine_override(stub):
+        assert m._get_engine() is stub
+        for k in range(20):
+            th = _sample_from_prior(m) * (1.0 if k < 15 else 2.5)
+            f_ref, g_ref = obj.fun(th)
+            f, g = fast.fun(th, stub.mll_grad)
+            if np.isfinite(f_ref):
+                assert abs(f - f_ref) <= 1e-12 * max(1.0, abs(f_ref))
+                assert np.max(np.abs(g - g_ref)) <= 1e-11 * max(1.0, np.max(np.abs(g_ref)))
+    assert getattr(m, "_engine_stub", None) is None and "_get_engine" not in m.__dict__   # nothing left patched
 
 
 def test_host_objective_falls_back_for_unsupported_models():
