@@ -17,6 +17,12 @@
 //      a level is independent, so a level is two batched GEMM launches (ceil(log2 T) levels).  The part that
 //      only needs the leading tile columns of L starts behind the factorisation on a third stream.
 //   3. lauum: K^-1 = M^T M, one launch over the lower tiles (the upper triangle is not stored on the hot path).
+//
+// From N = 3072 the O(N^3) parts of all three steps run as exact integer GEMMs on the INT8 tcgen05 tensor cores
+// (oz_gemm.cuh / oz_split.cuh / oz_chol.cuh) when the handle carries an OzCtx: the trailing updates (and, from
+// N = 12288, the panel solve of the lazy-panel schedule potrf_lazy, whose diagonal blocks are factored by one
+// dataflow launch, block_potrf_kernel), the levels hb >= 4 of the inverse, and K^-1.  Everything latency-bound
+// (leaf, TRSM and updates inside a diagonal block, small levels) stays on the DMMA kernels of this file.
 #pragma once
 #include <stdio.h>
 #include <stdlib.h>
