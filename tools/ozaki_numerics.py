@@ -20,41 +20,15 @@ S = int(sys.argv[2]) if len(sys.argv) > 2 else 7      # digit planes per operand
 LEVELS = int(sys.argv[3]) if len(sys.argv) > 3 else S  # keep pairs with i + j < LEVELS
 
 
-def split_rows(A):
-    """A [rows, K] -> digits [S, rows, K] (float64 holding integers in [-128, 127]) and exponents e[rows] with
-    A = 2^e * sum_k digits[k] 256^-(k+1) + O(2^e 256^-S / 2).  Row max is mapped into [0.125, 0.25)."""
-    amax = np.max(np.abs(A), axis=1)
-    _, ex = np.frexp(amax)                      # amax = m 2^ex, m in [0.5, 1)
-    e = np.where(amax > 0, ex + 2, 0).astype(np.int64)
-    r = np.ldexp(A, -e[:, None])                # |r| < 0.25
-    planes = np.empty((S,) + A.shape)
-    for k in range(S):
-        x = r * 256.0
-        d = np.maximum(np.floor(x + 128.0 / 255.0), -128.0)   # remainder in [-128/255, 127/255]: next digit fits int8
-        assert d.max() <= 127.0, d.max()
-        planes[k] = d
-        r = x - d
-    return planes, e
+from oracle import oz_oracle as OZ  # noqa: E402
 
-
-LEVELS_KINV = int(os.environ.get("LEVELS_KINV", LEVELS))   # levels kept in K^-1 = M^T M only
+LEVELS_KINV = int(os.environ.get("LEVELS_KINV", LEVELS))    # levels kept in K^-1 = M^T M only
 LEVELS_TRTRI = int(os.environ.get("LEVELS_TRTRI", LEVELS))  # levels kept in the triangular inverse only
 
 
 def ozaki_abt(A, B, levels=None):
-    """A [m,K] @ B[n,K]^T through digit planes."""
-    levels = LEVELS if levels is None else levels
-    pa, ea = split_rows(A)
-    pb, eb = split_rows(B)
-    acc = np.zeros((A.shape[0], B.shape[0]))
-    for lvl in range(levels - 1, -1, -1):       # small terms first
-        t = np.zeros_like(acc)
-        for i in range(min(lvl, S - 1) + 1):
-            j = lvl - i
-            if j < S:
-                t += pa[i] @ pb[j].T
-        acc += np.ldexp(t, -8 * (lvl + 2))
-    return np.ldexp(acc, (ea[:, None] + eb[None, :]))
+    """A [m,K] @ B[n,K]^T through digit planes (oracle/oz_oracle.py)."""
+    return OZ.abt(A, B, LEVELS if levels is None else levels, S)
 
 
 def chol_blocked(K, nb, mm):
