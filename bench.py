@@ -392,8 +392,8 @@ def run_ours(args):
         peak_i8 = E.probe_i8(256, 4096, local)     # raw tcgen05 kind::i8 issue rate, whole GPU, measured live
         peak_i8_n128 = E.probe_i8(128, 4096, local)
         pairs = 28.0                                # int8 multiply-adds per FP64-equivalent multiply-add
-        kinv_pairs = {7: 28.0, 6: 21.0, 5: 15.0}.get(int(os.environ.get("GPP_OZ_KINV_LEVELS", "6")), 28.0)  # K^-1 product
-        ops_eval = (2.0 * pairs + kinv_pairs) * n3 / 3.0   # potrf + trtri with 28 plane pairs, K^-1 with 21
+        kinv_pairs = {7: 28.0, 6: 21.0, 5: 15.0}.get(int(os.environ.get("GPP_OZ_KINV_LEVELS", "7")), 28.0)  # K^-1 product
+        ops_eval = (2.0 * pairs + kinv_pairs) * n3 / 3.0   # potrf + trtri with 28 plane pairs, K^-1 with 28 (21 with GPP_OZ_KINV_LEVELS=6)
         ach_i8 = ops_eval / (tensor_ms * 1e-3) / 1e12
         roofline = {
             "bound": "tensor", "kernel": "oz_gemm_kernel (tcgen05.mma kind::i8 M=N=128 K=32, TMA-fed, int32 TMEM "
@@ -405,9 +405,9 @@ def run_ours(args):
                            "MEASURED_PEAKS.json has no INT8 entry (nominal 4500)" % peak_i8_n128,
             "algorithmic_ops_per_eval": ops_eval,
             "basis": "all O(N^3) work of one step: N^3 FP64-equivalent flops (potrf + trtri + lauum, N^3/3 each) = "
-                     "(28 + 28 + 21) N^3 / 3 int8 ops actually issued (28 plane pairs per product; K^-1, which only feeds the "
-                     "gradient trace, keeps 21), over the CUDA-event time of those three stages (digit-plane splits, DMMA "
-                     "panel chain, leaf kernels and launch gaps included)",
+                     "(28 + 28 + %d) N^3 / 3 int8 ops actually issued (28 plane pairs per product; K^-1, which only feeds the "
+                     "gradient trace, can run with 21: GPP_OZ_KINV_LEVELS=6), over the CUDA-event time of those three stages (digit-plane splits, DMMA "
+                     "panel chain, leaf kernels and launch gaps included)" % kinv_pairs,
             "largest_launch": {"what": "K^-1 = L^-T L^-1: transposed digit-plane split + one oz_gemm launch, %d plane pairs" % kinv_pairs,
                                "algorithmic_ops": kinv_pairs * n3 / 3, "ms": stage["lauum"],
                                "achieved": kinv_pairs * n3 / 3 / (stage["lauum"] * 1e-3) / 1e12,

@@ -26,9 +26,11 @@ struct OzCtx {
     static constexpr int LAZY_PB = 16;     // widest panel in 128-tiles (sizes the W planes)
     int lazy_pb = 12;                      // panel width used (GPP_OZ_LAZY_PB)
     int lazy = 1;
-    int kinv_levels = 6;           // significance levels of K^-1 = M^T M (GPP_OZ_KINV_LEVELS): its only consumer is the
-                                   // gradient trace (tolerance 1e-8 of the gradient's max-norm); 21 of 28 plane pairs
-                                   // move the gradient by ~1e-12 (tools/ozaki_numerics.py, LEVELS_KINV)
+    int kinv_levels = 7;           // significance levels of K^-1 = M^T M (GPP_OZ_KINV_LEVELS).  Its only consumer is the
+                                   // gradient trace (tolerance 1e-8 of the gradient's max-norm): with 6 levels (21 of 28
+                                   // plane pairs) the product takes 11.1 instead of 13.4 ms at N = 16384 and the gradient
+                                   // moves by 6.6e-11 instead of 2.9e-13.  Default 7: both arithmetics then agree at the
+                                   // FP64 rounding level and multi-start fits follow the same L-BFGS-B paths
     int lazy_min_tiles = 96;       // from N = 12288; below, 512-column panels of the look-ahead schedule keep the chain
                                    // shorter (measured: N = 8192 12.7 vs 14.0 ms, N = 12288 28.5 vs 27.9, N = 16384 55.3 vs 54.4)
     int stagger = 6000;            // ns per 128-block of K: estimated duration of one 128x128 item, see OzGemmOp.stagger_ns
